@@ -1,0 +1,280 @@
+/*
+ * ssam_gpu.h -- C-ABI of the B200-native constitutive + heat-source update
+ *               (grad(U) -> strain rate -> viscoplastic nu -> two-phase mixture -> heat sources)
+ *
+ * Drop-in boundary for ONE hot path of kckincaid/solidStateAMFoam's chtMultiRegionInterFoam.
+ * The reference has no FFI: the path sits behind OpenFOAM run-time-selectable C++ virtuals.
+ * Every entry point below names the reference interface (file:line under /root/reference) it
+ * replaces; INTEGRATION.md shows the OpenFOAM-side shim that forwards to it.
+ *
+ * Conventions
+ *   - plain C, opaque handle, int status (0 = ok); no exceptions cross the boundary;
+ *     ssam_last_error() returns the message of the last failing call on that context.
+ *   - scalar = double (WM_PRECISION_OPTION=DP), label = int32 (WM_LABEL_SIZE=32).
+ *   - host buffers are caller-owned and borrowed for the duration of the call; host layout is
+ *     OpenFOAM's contiguous AoS Field<T>: vector = 3 doubles (x,y,z), tensor = 9 doubles row-major.
+ *   - every field has an internal part (nCells) and a boundary part (nFaces-nInternalFaces values in
+ *     boundary-face order = patch order), like a GeometricField.
+ *   - one context per rank / GPU; calls on one context are serialised by the caller (as in OpenFOAM).
+ *   - there is NO CPU fallback: every compute entry point launches sm_100a kernels or fails.
+ */
+#ifndef SSAM_GPU_H
+#define SSAM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SSAM_API __attribute__((visibility("default")))
+#else
+#define SSAM_API
+#endif
+
+typedef struct ssam_ctx ssam_ctx;
+typedef int ssam_status;
+
+enum {
+    SSAM_OK = 0,
+    SSAM_ERR_INVALID = 1,   /* bad argument / call order                                   */
+    SSAM_ERR_CUDA = 2,      /* CUDA runtime error (message has the cudaError string)       */
+    SSAM_ERR_UNKNOWN_MODEL = 3, /* mirrors FatalError "Unknown ... model" (stickModelNew.C:46-54) */
+    SSAM_ERR_MISSING_FIELD = 4, /* mirrors objectRegistry::lookupObject failure (constantSlipStick.C:72) */
+    SSAM_ERR_COMM = 5,      /* NCCL failure / communicator missing                          */
+    SSAM_ERR_UNITS = 6      /* mirrors "Unknown conductivity function units"
+                               (incompressibleTwoPhaseThermalMixture.C:235-238,305-308)     */
+};
+
+/* ---- patches ---------------------------------------------------------------------------------- */
+enum { SSAM_PATCH_GENERIC = 0, SSAM_PATCH_PROCESSOR = 1, SSAM_PATCH_EMPTY = 2 };
+
+/* how snGrad(U) is formed on a non-coupled patch (gaussGrad boundary correction):
+ * VALUE: deltaCoeffs*(U_b - U_P) (fixedValue family incl. constant/exponentialRotationalSlip);
+ * ZERO_GRADIENT: 0. Processor patches ignore this. */
+enum { SSAM_BC_VALUE = 0, SSAM_BC_ZERO_GRADIENT = 1 };
+
+/* ---- mesh --------------------------------------------------------------------------------------
+ * Replaces the fvMesh accessors the path reads: owner()/neighbour() and Sf()/weights()/V() inside
+ * fvc::grad(U) (called at fluid/TEqn.H:3, stickModel.C:60, NortonHoff.C:62), C()/Cf()/magSf() and
+ * patch faceCells in constantSlipStick.C:110-146, patch Cf in
+ * constantRotationalSlipFvPatchVectorField.C:109-139.  Geometry is an input (never recomputed). */
+typedef struct ssam_mesh_desc {
+    int32_t nCells, nInternalFaces, nFaces, nPatches;
+    const int32_t* owner;        /* [nFaces]                                                       */
+    const int32_t* neighbour;    /* [nInternalFaces]                                               */
+    const int32_t* patchStart;   /* [nPatches] first (global) face of the patch                    */
+    const int32_t* patchSize;    /* [nPatches]                                                     */
+    const int32_t* patchKind;    /* [nPatches] SSAM_PATCH_*                                        */
+    const int32_t* patchNbrRank; /* [nPatches] neighbour rank of a processor patch, else -1        */
+    const double* Sf;            /* [3*nFaces] face area vectors (owner->neighbour / outward)      */
+    const double* weights;       /* [nFaces] linear weights: internal faces, then patch weights    */
+    const double* V;             /* [nCells]                                                       */
+    const double* C;             /* [3*nCells] cell centres                                        */
+    const double* Cf_b;          /* [3*nBnd] boundary face centres                                 */
+    const double* magSf_b;       /* [nBnd]                                                         */
+    const double* deltaCoeffs_b; /* [nBnd]                                                         */
+} ssam_mesh_desc;
+
+/* ---- fields ------------------------------------------------------------------------------------
+ * The registry names the reference looks up ("temp", "epsilonDotEq", "muEff", "sigmay", alphaName,
+ * pName: SheppardWright.C:55,58; constantSlipStick.C:54-75) become field ids. */
+enum {
+    SSAM_F_U = 0,        /* vector, in                                                             */
+    SSAM_F_T = 1,        /* "temp", in                                                             */
+    SSAM_F_ALPHA1 = 2,   /* alpha.<phase1>, in                                                     */
+    SSAM_F_P = 3,        /* pName, in (friction only)                                              */
+    SSAM_F_EPSDOT = 4,   /* "epsilonDotEq" = sqrt(2/3)|symm(grad U)|  (fluid/TEqn.H:3)             */
+    SSAM_F_NU1 = 5,      /* phase-1 viscosityModel nu_                                             */
+    SSAM_F_NU2 = 6,      /* phase-2 viscosityModel nu_                                             */
+    SSAM_F_SIGMAF = 7,   /* "sigmaf"                                                               */
+    SSAM_F_SIGMAY = 8,   /* "sigmay"                                                               */
+    SSAM_F_NU = 9,       /* mixture nu_ (incompressibleTwoPhaseThermalMixture.C:53)                */
+    SSAM_F_MUEFF = 10,   /* "muEff" = thermo.mu() (fluid/TEqn.H:6)                                 */
+    SSAM_F_RHO = 11,     /* thermo.rho()                                                           */
+    SSAM_F_CP = 12,      /* thermo.cp()  (fluid/TEqn.H:12)                                         */
+    SSAM_F_K = 13,       /* thermo.k()   (fluid/TEqn.H:15)                                         */
+    SSAM_F_QVISC = 14,   /* friction.qvisc()                                                       */
+    SSAM_F_QFRIC = 15,   /* friction.qfric()                                                       */
+    SSAM_F_GRADU = 16,   /* tensor, fvc::grad(U) (debug / parity / calculateStrain.H)              */
+    SSAM_F_STRAINRATE = 17, /* viscosityModel::strainRate() = sqrt(2)|symm(grad U)| (NortonHoff.C:62) */
+    SSAM_F_RHO_SOLVER = 18, /* rho   == alpha1*rho1 + alpha2*rho2        (alphaEqnSubCycle.H:41)    */
+    SSAM_F_RHOCP = 19,      /* rhoCp == alpha1*rho1*cp1 + alpha2*rho2*cp2 (alphaEqnSubCycle.H:42)   */
+    SSAM_F_COUNT = 20
+};
+
+/* ---- model parameters (what the reference reads from dictionaries) ---------- */
+enum { SSAM_VISC_NEWTONIAN = 0, SSAM_VISC_SHEPPARD_WRIGHT = 1, SSAM_VISC_FKS = 2, SSAM_VISC_NORTON_HOFF = 3 };
+
+typedef struct ssam_viscosity_params {
+    int32_t model; /* SSAM_VISC_* */
+    int32_t _pad;
+    /* Newtonian: nu */
+    double nu;
+    /* SheppardWright (SheppardWright.C:132-138; limiters :104-106) */
+    double sigmaR, Q, R, A, n;
+    /* FKS (FKS.C:199-213) */
+    double a1, a2, b1, b2, b3, e0, c1, c2, Tm, Ta;
+    /* NortonHoff (NortonHoff.C:82-88) */
+    double mu0, m, strainRateEffMin;
+    /* common */
+    double rho, nuMin, nuMax, eDotMin;
+} ssam_viscosity_params;
+
+enum { SSAM_K_CONSTANT = 0, SSAM_K_CUBIC = 1 };
+enum { SSAM_UNITS_KELVIN = 0, SSAM_UNITS_CELSIUS = 1 };
+
+typedef struct ssam_conductivity {
+    int32_t kModel; /* SSAM_K_*  (kModel word, incompressibleTwoPhaseThermalMixture.C:108-109) */
+    int32_t units;  /* SSAM_UNITS_* (:223-239); any other value -> SSAM_ERR_UNITS             */
+    double k;       /* constant model (:261)                                                   */
+    double k0, k1, k2, k3, Tmin, Tmax; /* cubic model (:215-221)                               */
+} ssam_conductivity;
+
+typedef struct ssam_mixture_params {
+    double rho1, rho2, cp1, cp2; /* incompressibleTwoPhaseThermalMixture.C:100-106 */
+    ssam_conductivity k1, k2;
+} ssam_mixture_params;
+
+enum { SSAM_STICK_CONSTANT = 0, SSAM_STICK_EXPONENTIAL = 1 };
+
+typedef struct ssam_stick_params {
+    int32_t model;     /* SSAM_STICK_*: constantSlipStick / exponentialSlipStick                  */
+    int32_t fricPatch; /* patch index of `fricPatch`; <0 skips qfric (NortonHoff case, SURVEY D-1) */
+    double betaTQ;
+    double omega[3];
+    double delta, muf;                    /* constantSlipStick.C:165-168                          */
+    double omega0, delta0, Rs, mu0, lambda; /* exponentialSlipStick.C ctor                         */
+} ssam_stick_params;
+
+enum { SSAM_ROTSLIP_CONSTANT = 0, SSAM_ROTSLIP_EXPONENTIAL = 1 };
+
+typedef struct ssam_rotslip_params {
+    int32_t model; /* SSAM_ROTSLIP_* */
+    int32_t patch;
+    double omega[3];
+    double Vt[3];
+    double delta;              /* constantRotationalSlip   */
+    double omega0, delta0, R0; /* exponentialRotationalSlip */
+} ssam_rotslip_params;
+
+/* everything one fused update needs (benchmark path) */
+typedef struct ssam_update_params {
+    ssam_viscosity_params visc1, visc2;
+    ssam_mixture_params mix;
+    ssam_stick_params stick;
+} ssam_update_params;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+SSAM_API ssam_status ssam_create(ssam_ctx** ctx, int device);
+SSAM_API ssam_status ssam_destroy(ssam_ctx* ctx);
+SSAM_API const char* ssam_last_error(const ssam_ctx* ctx); /* ctx may be NULL (creation errors) */
+SSAM_API ssam_status ssam_sync(ssam_ctx* ctx);
+/* Launch on the caller's CUDA stream (cudaStream_t as void*; NULL = the context's own stream) and
+ * choose whether compute calls block until done (default 1, OpenFOAM semantics). */
+SSAM_API ssam_status ssam_set_stream(ssam_ctx* ctx, void* cuda_stream);
+SSAM_API ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking);
+SSAM_API int ssam_abi_version(void);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+SSAM_API int64_t ssam_launch_count(const ssam_ctx* ctx);
+
+/* ---- mesh + integer addressing ------------------------------------------------------------------ */
+SSAM_API ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* mesh);
+/* per-patch snGrad kind of U, [nPatches] of SSAM_BC_*; default SSAM_BC_VALUE */
+SSAM_API ssam_status ssam_patch_u_bc_set(ssam_ctx* ctx, const int32_t* kinds);
+
+/* Derived addressing, built on the GPU by ssam_mesh_set; getters exist for the bit-exact integer
+ * parity checks ("integer work ... must be bit-exact", BASELINE.json north_star). */
+enum {
+    SSAM_ADDR_OWNER_START = 0,  /* [nCells+1] first owned internal face of each cell (lduAddressing ownerStart) */
+    SSAM_ADDR_EXTRA_START = 1,  /* [nCells+1] offsets into the extra list                                     */
+    SSAM_ADDR_EXTRA_FACE = 2,   /* [nExtra] neighbour-side internal faces (ascending) then boundary faces
+                                   (ascending) of each cell                                                    */
+    SSAM_ADDR_EXTRA_OTHER = 3,  /* [nExtra] owner cell of that face; -1 generic boundary, -2 coupled boundary  */
+    SSAM_ADDR_CELL_FACES_START = 4, /* [nCells+1] full cell->face CSR, ascending face index                  */
+    SSAM_ADDR_CELL_FACES = 5,   /* [nIF*2+nBnd] face index, bit 31 set when the cell is the neighbour        */
+    SSAM_ADDR_HALO_SEND_CELLS = 6, /* [nProcFaces] faceCells of all processor patches, patch order           */
+    SSAM_ADDR_HALO_PATCH_OFFSETS = 7, /* [nProcPatches+1] offsets of each processor patch in the send list   */
+    SSAM_ADDR_FRIC_CELLS = 8,   /* [patchSize] faceCells of the last friction patch used                     */
+    SSAM_ADDR_FACE_COLOUR = 9,  /* [nInternalFaces] greedy face colouring (scatter variant)                  */
+    SSAM_ADDR_COUNT = 10
+};
+SSAM_API ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n);
+SSAM_API ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t n);
+
+/* ---- field transfer ----------------------------------------------------------------------------- */
+/* host AoS -> device SoA (transposed on the device); either pointer may be NULL to skip that part */
+SSAM_API ssam_status ssam_field_upload(ssam_ctx* ctx, int field, const double* internal, const double* boundary);
+SSAM_API ssam_status ssam_field_download(ssam_ctx* ctx, int field, double* internal, double* boundary);
+/* device-resident use: pointer to component plane `comp` (length nCells+nBnd: internal then boundary) */
+SSAM_API ssam_status ssam_field_device_ptr(ssam_ctx* ctx, int field, int comp, void** ptr, int64_t* len);
+/* 1 if the field currently holds data (uploaded or computed) */
+SSAM_API int ssam_field_is_set(const ssam_ctx* ctx, int field);
+
+/* ---- boundary conditions feeding the gradient ---------------------------------------------------
+ * constantRotationalSlipFvPatchVectorField::updateCoeffs (…C:109-139) and
+ * exponentialRotationalSlipFvPatchVectorField::updateCoeffs (…C:119-153): writes U_b on `patch`. */
+SSAM_API ssam_status ssam_bc_rotational_slip(ssam_ctx* ctx, const ssam_rotslip_params* p);
+
+/* ---- staged entry points (drop-in; each equals one reference call) ------------------------------ */
+/* fvc::grad(U) with "Gauss linear" incl. boundary correction -> SSAM_F_GRADU (calculateStrain.H:17) */
+SSAM_API ssam_status ssam_grad_u(ssam_ctx* ctx);
+/* out_field = factor*mag(symm(fvc::grad(U))):  fluid/TEqn.H:3 (factor sqrt(2/3) -> SSAM_F_EPSDOT),
+ * stickModel.C:58-61 / viscosityModel::strainRate() (factor sqrt(2) -> SSAM_F_STRAINRATE) */
+SSAM_API ssam_status ssam_strain_rate(ssam_ctx* ctx, double factor, int out_field);
+/* viscosityModel::correct() of phase 1 or 2: SheppardWright.H:133-138, FKS.H:156-161,
+ * NortonHoff.H:126-129 (recomputes strainRate() from U), Newtonian (constant). Reads T, EPSDOT. */
+SSAM_API ssam_status ssam_viscosity_correct(ssam_ctx* ctx, int phase, const ssam_viscosity_params* p);
+/* incompressibleTwoPhaseThermalMixture::calcNu tail (…C:46-53): NU = mu()/(la*rho1+(1-la)*rho2) */
+SSAM_API ssam_status ssam_mixture_calc_nu(ssam_ctx* ctx, const ssam_mixture_params* p);
+/* thermo.correct() = nuModel1.correct(); nuModel2.correct(); calcNu tail
+ * (immiscibleIncompressibleTwoPhaseThermalMixture.H:77-81 minus interfaceProperties::correct()) */
+SSAM_API ssam_status ssam_thermo_correct(ssam_ctx* ctx, const ssam_viscosity_params* v1,
+                                         const ssam_viscosity_params* v2, const ssam_mixture_params* mix);
+/* thermo.mu()/rho()/cp()/k() (…C:133-153, 384-400, 365-381, 346-362) -> MUEFF / RHO / CP / K */
+SSAM_API ssam_status ssam_mixture_mu(ssam_ctx* ctx, const ssam_mixture_params* p);
+SSAM_API ssam_status ssam_mixture_rho(ssam_ctx* ctx, const ssam_mixture_params* p);
+SSAM_API ssam_status ssam_mixture_cp(ssam_ctx* ctx, const ssam_mixture_params* p);
+SSAM_API ssam_status ssam_mixture_k(ssam_ctx* ctx, const ssam_mixture_params* p);
+/* solver-side rho, rhoCp (multiRegionVoF/alphaEqnSubCycle.H:41-42) -> RHO_SOLVER, RHOCP */
+SSAM_API ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p);
+/* frictionModel::correct() -> stickModel::correct(): qvisc_, qfric_ (constantSlipStick.H:133-138,
+ * exponentialSlipStick.H:139-144). Reads MUEFF, EPSDOT, ALPHA1, SIGMAY, P. */
+SSAM_API ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p);
+/* patch centroid of the friction patch after the cross-rank sum (constantSlipStick.C:118-138) */
+SSAM_API ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* area);
+
+/* ---- fused entry point (the benchmarked path) ---------------------------------------------------
+ * One pass: grad(U) -> EPSDOT -> nuModel1/2.correct() (NU1,SIGMAF,SIGMAY,NU2) -> NU -> MUEFF ->
+ * QVISC,QFRIC -> RHO,CP,K.  Per-field results equal the staged calls issued in that order on the
+ * same inputs.  `flags`: bit 0 also write SSAM_F_GRADU. */
+SSAM_API ssam_status ssam_update_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags);
+/* Host-staged drop-in of the same update: uploads U,T,alpha1,p (AoS host buffers, internal+boundary),
+ * runs the fused kernels, downloads the listed output fields. Used for the e2e metric. */
+typedef struct ssam_host_io {
+    const double* U_i; const double* U_b;
+    const double* T_i; const double* T_b;
+    const double* alpha1_i; const double* alpha1_b;
+    const double* p_i; const double* p_b;   /* may be NULL when qfric is skipped */
+    int32_t nOut;
+    const int32_t* outFields;  /* [nOut] SSAM_F_* */
+    double* const* out_i;      /* [nOut] host internal buffers */
+    double* const* out_b;      /* [nOut] host boundary buffers (entries may be NULL) */
+} ssam_host_io;
+SSAM_API ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io);
+
+/* ---- multi-GPU: processor-patch halos over NCCL --------------------------------------------------
+ * Replaces processorFvPatchField initEvaluate/evaluate (OpenFOAM, triggered by
+ * correctBoundaryConditions()) and the reduce() pair in constantSlipStick.C:134-135. */
+#define SSAM_UNIQUE_ID_BYTES 128
+SSAM_API ssam_status ssam_comm_unique_id(void* id_out /* SSAM_UNIQUE_ID_BYTES */);
+SSAM_API ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int nRanks);
+/* boundary values on processor patches <- neighbour rank's adjacent cell values, for every field
+ * whose bit (1<<SSAM_F_*) is set in field_mask */
+SSAM_API ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t field_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSAM_GPU_H */

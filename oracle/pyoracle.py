@@ -1,0 +1,179 @@
+"""ctypes wrapper of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; never by the product package.  See oracle/oracle.cpp for what the oracle is (a CPU restatement,
+parity unpinned by the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from solidstateamfoam_b200 import params as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+FAITHFUL, FUSED = 0, 1
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        src = os.path.join(_HERE, "oracle.cpp")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+        L = C.CDLL(so)
+        vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [C.POINTER(P.MeshDesc), ip]
+        L.orc_destroy.argtypes = [vp]
+        L.orc_last_error.restype = C.c_char_p
+        L.orc_last_error.argtypes = [vp]
+        L.orc_field.restype = dp
+        L.orc_field.argtypes = [vp, C.c_int, C.c_int]
+        L.orc_ntot.argtypes = [vp]
+        L.orc_bc_rotational_slip.argtypes = [vp, C.POINTER(P.RotSlipParams)]
+        L.orc_grad_u.argtypes = [vp, C.c_int]
+        L.orc_strain_rate.argtypes = [vp, C.c_double, C.c_int, C.c_int]
+        L.orc_strain_from_grad.argtypes = [vp, C.c_double, C.c_int, C.c_int]
+        L.orc_viscosity_correct.argtypes = [vp, C.c_int, C.POINTER(P.ViscosityParams), C.c_int]
+        for n in ("calc_nu", "mu", "rho", "cp", "k"):
+            getattr(L, "orc_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
+        L.orc_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
+        L.orc_friction_patch_sums.argtypes = [vp, C.c_int, dp]
+        L.orc_friction_correct.argtypes = [vp, C.POINTER(P.StickParams), dp, C.c_int]
+        L.orc_friction_patch_centre.argtypes = [vp, dp, dp]
+        L.orc_update.argtypes = [vp, C.POINTER(P.UpdateParams), dp, C.c_int]
+        L.orc_addressing_size.restype = C.c_int64
+        L.orc_addressing_size.argtypes = [vp, C.c_int]
+        L.orc_addressing_get.argtypes = [vp, C.c_int, ip]
+        L.orc_halo_exchange.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+        L.orc_update_multi.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(P.UpdateParams), C.c_int]
+        _lib = L
+    return _lib
+
+
+class OracleError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"oracle status {status}: {msg}")
+        self.status = status
+
+
+class OracleCase:
+    """One mesh (partition) + its fields on the CPU."""
+
+    def __init__(self, mesh, patch_u_bc=None):
+        self.mesh = mesh
+        self._desc, self._keep = P.mesh_desc(mesh)
+        bc = None
+        if patch_u_bc is not None:
+            self._bc = np.ascontiguousarray(patch_u_bc, dtype=np.int32)
+            bc = self._bc.ctypes.data_as(C.POINTER(C.c_int32))
+        self.h = C.c_void_p(lib().orc_create(C.byref(self._desc), bc))
+        self.nTot = mesh.nCells + mesh.nBoundaryFaces
+
+    def close(self):
+        if self.h:
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st != 0:
+            raise OracleError(st, lib().orc_last_error(self.h).decode())
+
+    def field(self, f, mark=False) -> np.ndarray:
+        """numpy view [nTot, ncomp] (or [nTot]) into the oracle's storage: internal then boundary."""
+        nc = P.ncomp(f)
+        ptr = lib().orc_field(self.h, f, 1 if mark else 0)
+        a = np.ctypeslib.as_array(ptr, shape=(self.nTot * nc,))
+        return a.reshape(self.nTot, nc) if nc > 1 else a
+
+    def set(self, f, internal, boundary=None):
+        a = self.field(f, mark=True)
+        n = self.mesh.nCells
+        a[:n] = internal
+        if boundary is not None:
+            a[n:] = boundary
+
+    def internal(self, f):
+        return self.field(f)[: self.mesh.nCells].copy()
+
+    def boundary(self, f):
+        return self.field(f)[self.mesh.nCells:].copy()
+
+    # staged calls -------------------------------------------------------------------------------
+    def bc_rotational_slip(self, p):
+        self._chk(lib().orc_bc_rotational_slip(self.h, C.byref(p)))
+
+    def grad_u(self, form=FAITHFUL):
+        self._chk(lib().orc_grad_u(self.h, form))
+
+    def strain_rate(self, factor, out_field, form=FAITHFUL):
+        self._chk(lib().orc_strain_rate(self.h, factor, out_field, form))
+
+    def strain_from_grad(self, factor, out_field, form=FAITHFUL):
+        self._chk(lib().orc_strain_from_grad(self.h, factor, out_field, form))
+
+    def viscosity_correct(self, phase, p, form=FAITHFUL):
+        self._chk(lib().orc_viscosity_correct(self.h, phase, C.byref(p), form))
+
+    def mixture(self, what, p, form=FAITHFUL):
+        self._chk(getattr(lib(), "orc_mixture_" + what)(self.h, C.byref(p), form))
+
+    def solver_rho_rhocp(self, p, form=FAITHFUL):
+        self._chk(lib().orc_solver_rho_rhocp(self.h, C.byref(p), form))
+
+    def friction_patch_sums(self, patch):
+        out = np.zeros(4)
+        lib().orc_friction_patch_sums(self.h, patch, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def friction_correct(self, p, sums=None, form=FAITHFUL):
+        s = None
+        if sums is not None:
+            s = np.ascontiguousarray(sums, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        self._chk(lib().orc_friction_correct(self.h, C.byref(p), s, form))
+
+    def friction_patch_centre(self):
+        c = np.zeros(3)
+        a = C.c_double()
+        lib().orc_friction_patch_centre(self.h, c.ctypes.data_as(C.POINTER(C.c_double)), C.byref(a))
+        return c, a.value
+
+    def update(self, p, sums=None, form=FAITHFUL):
+        s = None
+        if sums is not None:
+            s = np.ascontiguousarray(sums, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double))
+        self._chk(lib().orc_update(self.h, C.byref(p), s, form))
+
+    def addressing(self, which) -> np.ndarray:
+        n = lib().orc_addressing_size(self.h, which)
+        out = np.zeros(max(n, 0), dtype=np.int32)
+        lib().orc_addressing_get(self.h, which, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out
+
+
+def halo_exchange(cases, field):
+    arr = (C.c_void_p * len(cases))(*[c.h for c in cases])
+    st = lib().orc_halo_exchange(arr, len(cases), field)
+    if st:
+        raise OracleError(st, "halo exchange: processor patches do not match")
+
+
+def update_multi(cases, p, form=FAITHFUL):
+    """All ranks' update, one thread per rank, in-memory halo copies (the timed CPU baseline)."""
+    arr = (C.c_void_p * len(cases))(*[c.h for c in cases])
+    st = lib().orc_update_multi(arr, len(cases), C.byref(p), form)
+    if st:
+        raise OracleError(st, "; ".join(lib().orc_last_error(c.h).decode() for c in cases))

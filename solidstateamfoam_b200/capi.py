@@ -1,0 +1,266 @@
+"""ctypes binding of lib/libssam_gpu.so (include/ssam_gpu.h) -- what an FFI host would bind.
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is present,
+construction fails loudly (SsamError).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+from . import params as P
+
+_lib = None
+
+# every exported symbol of include/ssam_gpu.h (checked by tests/test_abi_symbols.py)
+SYMBOLS = [
+    "ssam_create", "ssam_destroy", "ssam_last_error", "ssam_sync", "ssam_set_stream", "ssam_set_blocking",
+    "ssam_abi_version", "ssam_launch_count", "ssam_mesh_set", "ssam_patch_u_bc_set", "ssam_addressing_size",
+    "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
+    "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
+    "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
+    "ssam_solver_rho_rhocp", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
+    "ssam_update_fused_host", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
+]
+
+
+class SsamError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"ssam status {status}: {msg}")
+        self.status = status
+        self.msg = msg
+
+
+def lib_path() -> str:
+    return os.path.join(_build.LIB, "libssam_gpu.so")
+
+
+def load():
+    """Load libssam_gpu.so (building it in-tree first if the .so is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        _build.build_cuda()
+    if not os.path.exists(path):
+        raise SsamError(P.ERR_CUDA, f"{path} is missing: the CUDA extension is required, there is no fallback")
+    L = C.CDLL(path)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    L.ssam_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.ssam_destroy.argtypes = [vp]
+    L.ssam_last_error.restype = C.c_char_p
+    L.ssam_last_error.argtypes = [vp]
+    L.ssam_sync.argtypes = [vp]
+    L.ssam_set_stream.argtypes = [vp, vp]
+    L.ssam_set_blocking.argtypes = [vp, C.c_int]
+    L.ssam_launch_count.restype = C.c_int64
+    L.ssam_launch_count.argtypes = [vp]
+    L.ssam_mesh_set.argtypes = [vp, C.POINTER(P.MeshDesc)]
+    L.ssam_patch_u_bc_set.argtypes = [vp, ip]
+    L.ssam_addressing_size.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
+    L.ssam_addressing_get.argtypes = [vp, C.c_int, ip, C.c_int64]
+    L.ssam_field_upload.argtypes = [vp, C.c_int, dp, dp]
+    L.ssam_field_download.argtypes = [vp, C.c_int, dp, dp]
+    L.ssam_field_device_ptr.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]
+    L.ssam_field_is_set.argtypes = [vp, C.c_int]
+    L.ssam_bc_rotational_slip.argtypes = [vp, C.POINTER(P.RotSlipParams)]
+    L.ssam_grad_u.argtypes = [vp]
+    L.ssam_strain_rate.argtypes = [vp, C.c_double, C.c_int]
+    L.ssam_viscosity_correct.argtypes = [vp, C.c_int, C.POINTER(P.ViscosityParams)]
+    L.ssam_thermo_correct.argtypes = [vp, C.POINTER(P.ViscosityParams), C.POINTER(P.ViscosityParams),
+                                      C.POINTER(P.MixtureParams)]
+    for n in ("calc_nu", "mu", "rho", "cp", "k"):
+        getattr(L, "ssam_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams)]
+    L.ssam_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams)]
+    L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
+    L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
+    L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
+    L.ssam_update_fused_host.argtypes = [vp, C.POINTER(P.UpdateParams), C.POINTER(P.HostIO)]
+    L.ssam_comm_unique_id.argtypes = [vp]
+    L.ssam_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ssam_halo_exchange.argtypes = [vp, C.c_uint32]
+    _lib = L
+    return L
+
+
+def _dptr(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a
+
+
+FUSED_WRITE_GRAD = 1
+FUSED_HALO_INPUTS = 2
+
+
+class Context:
+    """One rank / one GPU.  Thin, 1:1 with the C entry points."""
+
+    def __init__(self, device: int = 0):
+        L = load()
+        self.L = L
+        h = C.c_void_p()
+        st = L.ssam_create(C.byref(h), device)
+        if st != 0:
+            raise SsamError(st, L.ssam_last_error(None).decode())
+        self.h = h
+        self.mesh = None
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ssam_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, st):
+        if st != 0:
+            raise SsamError(st, self.L.ssam_last_error(self.h).decode())
+
+    # lifecycle ------------------------------------------------------------------------------------
+    def sync(self):
+        self._chk(self.L.ssam_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._chk(self.L.ssam_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_blocking(self, blocking: bool):
+        self._chk(self.L.ssam_set_blocking(self.h, 1 if blocking else 0))
+
+    def launch_count(self) -> int:
+        return int(self.L.ssam_launch_count(self.h))
+
+    # mesh -----------------------------------------------------------------------------------------
+    def mesh_set(self, mesh, patch_u_bc=None):
+        desc, keep = P.mesh_desc(mesh)
+        self._chk(self.L.ssam_mesh_set(self.h, C.byref(desc)))
+        self.mesh = mesh
+        self.nCells, self.nBnd = mesh.nCells, mesh.nBoundaryFaces
+        self.nTot = self.nCells + self.nBnd
+        if patch_u_bc is not None:
+            bc = np.ascontiguousarray(patch_u_bc, dtype=np.int32)
+            self._chk(self.L.ssam_patch_u_bc_set(self.h, bc.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def addressing(self, which: int) -> np.ndarray:
+        n = C.c_int64()
+        self._chk(self.L.ssam_addressing_size(self.h, which, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.int32)
+        self._chk(self.L.ssam_addressing_get(self.h, which, out.ctypes.data_as(C.POINTER(C.c_int32)), n.value))
+        return out
+
+    # fields ---------------------------------------------------------------------------------------
+    def upload(self, field: int, internal=None, boundary=None):
+        i, b = _f64(internal), _f64(boundary)
+        nc = P.ncomp(field)
+        if i is not None:
+            assert i.size == self.nCells * nc, (i.shape, self.nCells, nc)
+        if b is not None:
+            assert b.size == self.nBnd * nc, (b.shape, self.nBnd, nc)
+        self._chk(self.L.ssam_field_upload(self.h, field, _dptr(i), _dptr(b)))
+
+    def download(self, field: int):
+        nc = P.ncomp(field)
+        shape_i = (self.nCells, nc) if nc > 1 else (self.nCells,)
+        shape_b = (self.nBnd, nc) if nc > 1 else (self.nBnd,)
+        i = np.empty(shape_i, dtype=np.float64)
+        b = np.empty(shape_b, dtype=np.float64)
+        self._chk(self.L.ssam_field_download(self.h, field, _dptr(i), _dptr(b)))
+        return i, b
+
+    def device_ptr(self, field: int, comp: int = 0) -> tuple[int, int]:
+        p = C.c_void_p()
+        n = C.c_int64()
+        self._chk(self.L.ssam_field_device_ptr(self.h, field, comp, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def is_set(self, field: int) -> bool:
+        return bool(self.L.ssam_field_is_set(self.h, field))
+
+    # compute --------------------------------------------------------------------------------------
+    def bc_rotational_slip(self, p: P.RotSlipParams):
+        self._chk(self.L.ssam_bc_rotational_slip(self.h, C.byref(p)))
+
+    def grad_u(self):
+        self._chk(self.L.ssam_grad_u(self.h))
+
+    def strain_rate(self, factor: float, out_field: int):
+        self._chk(self.L.ssam_strain_rate(self.h, factor, out_field))
+
+    def viscosity_correct(self, phase: int, p: P.ViscosityParams):
+        self._chk(self.L.ssam_viscosity_correct(self.h, phase, C.byref(p)))
+
+    def thermo_correct(self, v1, v2, mix):
+        self._chk(self.L.ssam_thermo_correct(self.h, C.byref(v1), C.byref(v2), C.byref(mix)))
+
+    def mixture(self, what: str, p: P.MixtureParams):
+        self._chk(getattr(self.L, "ssam_mixture_" + what)(self.h, C.byref(p)))
+
+    def solver_rho_rhocp(self, p: P.MixtureParams):
+        self._chk(self.L.ssam_solver_rho_rhocp(self.h, C.byref(p)))
+
+    def friction_correct(self, p: P.StickParams):
+        self._chk(self.L.ssam_friction_correct(self.h, C.byref(p)))
+
+    def friction_patch_centre(self):
+        c = np.zeros(3)
+        a = C.c_double()
+        self._chk(self.L.ssam_friction_patch_centre(self.h, _dptr(c), C.byref(a)))
+        return c, a.value
+
+    def update_fused(self, p: P.UpdateParams, flags: int = 0):
+        self._chk(self.L.ssam_update_fused(self.h, C.byref(p), flags))
+
+    def update_fused_host(self, p: P.UpdateParams, io: P.HostIO):
+        self._chk(self.L.ssam_update_fused_host(self.h, C.byref(p), C.byref(io)))
+
+    # comm -----------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = load()
+        buf = C.create_string_buffer(P.UNIQUE_ID_BYTES)
+        st = L.ssam_comm_unique_id(buf)
+        if st != 0:
+            raise SsamError(st, L.ssam_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        buf = C.create_string_buffer(uid, P.UNIQUE_ID_BYTES)
+        self._keep.append(buf)
+        self._chk(self.L.ssam_comm_init(self.h, buf, rank, n_ranks))
+
+    def halo_exchange(self, fields):
+        mask = 0
+        for f in fields:
+            mask |= 1 << f
+        self._chk(self.L.ssam_halo_exchange(self.h, mask))
+
+    # convenience ----------------------------------------------------------------------------------
+    def load_case(self, case, apply_bc=True):
+        """mesh + inputs of a cases.Case; the tool-patch U comes from the rotational-slip BC kernel."""
+        self.mesh_set(case.mesh, case.patch_u_bc)
+        self.upload(P.F_U, case.U_i, case.U_b)
+        self.upload(P.F_T, case.T_i, case.T_b)
+        self.upload(P.F_ALPHA1, case.alpha1_i, case.alpha1_b)
+        self.upload(P.F_P, case.p_i, case.p_b)
+        if apply_bc and case.rotslip is not None:
+            self.bc_rotational_slip(case.rotslip)

@@ -1,0 +1,235 @@
+"""Synthetic cases for BASELINE.json's five configs (SURVEY.md §8d "Concrete synthetic inputs").
+
+The reference ships no case files, so all material constants below are *our* choices (literature /
+placeholder magnitudes, flagged in SURVEY.md §8d); meshes come from mesh.py, fields are seeded
+(Philox, seed = 20261019 + cfg index).  Every config takes a `scale` so the same case runs at a size
+the CPU oracle finishes in seconds (parity tests) and at BASELINE.json's full size (bench).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import mesh as M
+from . import params as P
+
+SEED0 = 20261019
+OMEGA = (0.0, 0.0, 41.9)
+VT = (2e-3, 0.0, 0.0)
+
+
+@dataclass
+class Case:
+    name: str
+    mesh: M.Mesh
+    U_i: np.ndarray
+    U_b: np.ndarray
+    T_i: np.ndarray
+    T_b: np.ndarray
+    alpha1_i: np.ndarray
+    alpha1_b: np.ndarray
+    p_i: np.ndarray
+    p_b: np.ndarray
+    params: P.UpdateParams
+    rotslip: P.RotSlipParams | None
+    patch_u_bc: np.ndarray
+    outputs: list = field(default_factory=list)   # SSAM_F_* the fused update produces for this case
+    bytes_per_update: int = 0                     # algorithmic bytes, SURVEY §8d formula
+    meta: dict = field(default_factory=dict)
+
+
+def algorithmic_bytes(mesh: M.Mesh, n_fric: int, norton_hoff: bool) -> int:
+    """B = 40*N_if + 52*N_bf + 128*N_c + 40*N_fric  (112/cell for NortonHoff) -- SURVEY.md §8d."""
+    per_cell = 112 if norton_hoff else 128
+    return 40 * mesh.nInternalFaces + 52 * mesh.nBoundaryFaces + per_cell * mesh.nCells + 40 * n_fric
+
+
+def _fields(mesh: M.Mesh, seed: int, alpha_mode: str, z0: float | None = None, step: int = 0, dt: float = 1e-3,
+            box=None):
+    """U, T, alpha1, p at cell centres and boundary-face centres (boundary = 'calculated' values of the
+    same analytic fields; tool-patch U is overwritten by the rotational-slip BC afterwards)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    nc, nif = mesh.nCells, mesh.nInternalFaces
+    X = np.concatenate([mesh.C, mesh.Cf[nif:]], axis=0)
+    if box is None:
+        lo = X.min(axis=0)
+        hi = X.max(axis=0)
+    else:  # global box of a decomposed case, so the analytic fields are continuous across ranks
+        lo, hi = np.asarray(box[0], dtype=float), np.asarray(box[1], dtype=float)
+    L = hi - lo
+    xc = 0.5 * (lo + hi)
+    ztop = hi[2]
+    om = np.array(OMEGA)
+    # rigid rotation about the vertical axis through the top-patch centre, decaying with depth,
+    # rotated in phase by omega*dt*step, + 1e-3 noise  (near-rigid rotation = the AFSD stick zone,
+    # the worst case for summation-order sensitivity)
+    rel = X - np.array([xc[0], xc[1], 0.0])
+    ph = om[2] * dt * step
+    c, s = math.cos(ph), math.sin(ph)
+    rel = np.stack([c * rel[:, 0] - s * rel[:, 1], s * rel[:, 0] + c * rel[:, 1], rel[:, 2]], axis=1)
+    decay = np.exp(-(ztop - X[:, 2]) / (0.125 * L[2]))
+    U = np.cross(np.broadcast_to(om, rel.shape), rel) * decay[:, None]
+    U += 1e-3 * rng.uniform(-1.0, 1.0, size=U.shape) * (np.abs(om[2]) * 0.5 * L[0])
+    r2 = (X[:, 0] - xc[0]) ** 2 + (X[:, 1] - xc[1]) ** 2 + (X[:, 2] - ztop) ** 2
+    T = 300.0 + 500.0 * np.exp(-r2 / (0.3 * L[0]) ** 2) + 100.0 * step * dt
+    if z0 is None:
+        z0 = lo[2] + 0.6 * L[2]
+    # substrate below z0 plus a column of deposited material under the tool, so the friction patch
+    # (zmax) touches material (alpha1 = 1) inside the tool radius and air outside it
+    rxy = np.sqrt((X[:, 0] - xc[0]) ** 2 + (X[:, 1] - xc[1]) ** 2)
+    rtool = 0.3 * L[0]
+    if alpha_mode == "step":
+        alpha = np.where((X[:, 2] < z0) | (rxy < rtool), 1.0, 0.0)
+    else:  # smooth tanh interfaces overshooting [0,1] by 1e-3 to exercise the clamp
+        az = 0.5 * (1.0 - np.tanh((X[:, 2] - z0) / (0.02 * L[2])))
+        ar = 0.5 * (1.0 - np.tanh((rxy - rtool) / (0.02 * L[0])))
+        alpha = np.maximum(az, ar) * (1.0 + 2e-3) - 1e-3
+    p = 1e5 * (1.0 + 0.1 * rng.uniform(-1.0, 1.0, size=X.shape[0]))
+    return (np.ascontiguousarray(U[:nc]), np.ascontiguousarray(U[nc:]), T[:nc].copy(), T[nc:].copy(),
+            alpha[:nc].copy(), alpha[nc:].copy(), p[:nc].copy(), p[nc:].copy())
+
+
+AIR = dict(nu=1.5e-5, rho=1.2, cp=1005.0, k=0.026)
+
+
+def sheppard_wright_aa6061():
+    # AA6061 literature constants (not in the reference)
+    return P.sheppard_wright(sigmaR=2.222e7, Q=1.45e5, R=8.314, A=2.409e8, n=3.55, rho=2700.0, nuMin=1e-6,
+                             nuMax=1e4, eDotMin=1e-6)
+
+
+def fks_placeholder():
+    return P.fks(a1=3.24e8, a2=1.14e8, b1=0.01, b2=1.0, b3=1.0, e0=1.0, c1=6.0, c2=1.0, Tm=855.0, Ta=293.0,
+                 rho=2700.0, nuMin=1e-6, nuMax=1e4, eDotMin=1e-6)
+
+
+def norton_hoff_placeholder():
+    return P.norton_hoff(mu0=1e8, m=0.2, rho=2700.0, nuMin=1e-6, nuMax=1e4, strainRateEffMin=1e-6)
+
+
+def _finish(name, mesh, flds, visc1, mix, stick, rotslip, seed, meta=None) -> Case:
+    top = mesh.patch_id("zmax")
+    bc = np.full(mesh.nPatches, P.BC_VALUE, dtype=np.int32)
+    # side walls zeroGradient, bottom + top fixedValue: exercises both snGrad kinds
+    for nm in ("xmin", "xmax", "ymin", "ymax"):
+        pid = mesh.patch_id(nm)
+        if pid >= 0:
+            bc[pid] = P.BC_ZERO_GRADIENT
+    up = P.UpdateParams(visc1=visc1, visc2=P.newtonian(AIR["nu"], AIR["rho"]), mix=mix, stick=stick)
+    nh = visc1.model == P.VISC_NORTON_HOFF
+    outs = [P.F_EPSDOT, P.F_NU1, P.F_NU2, P.F_NU, P.F_MUEFF, P.F_RHO, P.F_CP, P.F_K, P.F_QVISC]
+    if not nh:
+        outs += [P.F_SIGMAF, P.F_SIGMAY]
+    n_fric = 0
+    if stick.fricPatch >= 0:
+        outs.append(P.F_QFRIC)
+        n_fric = int(mesh.patchSize[stick.fricPatch])
+    U_i, U_b, T_i, T_b, a_i, a_b, p_i, p_b = flds
+    # zeroGradient patches carry U_b = U_P
+    for pid in range(mesh.nPatches):
+        if bc[pid] == P.BC_ZERO_GRADIENT and mesh.patchKind[pid] == P.PATCH_GENERIC:
+            U_b[mesh.patch_slice_b(pid)] = U_i[mesh.face_cells(pid)]
+    c = Case(name=name, mesh=mesh, U_i=U_i, U_b=U_b, T_i=T_i, T_b=T_b, alpha1_i=a_i, alpha1_b=a_b, p_i=p_i, p_b=p_b,
+             params=up, rotslip=rotslip, patch_u_bc=bc, outputs=outs,
+             bytes_per_update=algorithmic_bytes(mesh, n_fric, nh), meta=dict(meta or {}, seed=seed, top=top))
+    return c
+
+
+def _hex(dims, cell, side=(-1,) * 6, rank=0, origin=(0.0, 0.0, 0.0), affine=M.IDENTITY, grading=(1.0, 1.0, 1.0)):
+    nx, ny, nz = dims
+    return M.hex_block(nx, ny, nz, origin, (nx * cell, ny * cell, nz * cell), grading, affine, side, rank)
+
+
+def cfg1(dims=(64, 64, 32), step=0, affine=M.IDENTITY, grading=(1.0, 1.0, 1.0)) -> Case:
+    """hex 64x64x32, alpha1 step, SheppardWright AA6061, constantRotationalSlip + constantSlipStick."""
+    seed = SEED0 + 1
+    m = _hex(dims, 0.5e-3, affine=affine, grading=grading)
+    top = m.patch_id("zmax")
+    mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
+    stick = P.constant_slip_stick(top, betaTQ=0.9, delta=0.5, omega=OMEGA, muf=0.3)
+    rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
+    return _finish("cfg1", m, _fields(m, seed, "step", step=step), sheppard_wright_aa6061(), mix, stick, rot, seed)
+
+
+def cfg2(dims=(256, 256, 128), units="Kelvin", side=(-1,) * 6, rank=0, origin=(0.0, 0.0, 0.0), z0=None,
+         box=None) -> Case:
+    """hex 256x256x128, FKS + cubic k(T) for phase 1 (Kelvin or Celsius fit)."""
+    seed = SEED0 + 2 + rank
+    m = _hex(dims, 0.25e-3, side=side, rank=rank, origin=origin)
+    top = m.patch_id("zmax")
+    k1 = P.k_cubic(100.0, 0.2, -1e-4, 1e-8, 293.0 if units == "Kelvin" else 20.0,
+                   855.0 if units == "Kelvin" else 582.0, units)
+    mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], k1, P.k_constant(AIR["k"]))
+    if top >= 0:
+        stick = P.constant_slip_stick(top, betaTQ=0.9, delta=0.5, omega=OMEGA, muf=0.3)
+        rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
+    else:  # interior slab of a decomposed box: no tool patch on this rank
+        stick = P.no_friction_patch(0.9)
+        rot = None
+    return _finish("cfg2", m, _fields(m, seed, "tanh", z0=z0, box=box), fks_placeholder(), mix, stick, rot, seed,
+                   meta=dict(rank=rank))
+
+
+def cfg3(base=(128, 128, 128)) -> Case:
+    """~4M-cell polyhedral substrate+air mesh (2 levels of 2:1 refinement under the tool),
+    exponentialRotationalSlip BC + exponentialSlipStick friction heating, SheppardWright."""
+    seed = SEED0 + 3
+    nb = base
+    h = 0.4e-3 * 128 / nb[0]
+    L = (nb[0] * h, nb[1] * h, nb[2] * h)
+    m = M.poly_refined(nb[0], nb[1], nb[2], (0.0, 0.0, 0.0), L, r1=0.33 * L[0], d1=0.30 * L[2], r2=0.2 * L[0],
+                       d2=0.14 * L[2])
+    top = m.patch_id("zmax")
+    mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
+    stick = P.exponential_slip_stick(top, betaTQ=0.9, omega=OMEGA, omega0=41.9, delta0=0.3, Rs=19e-3, mu0=0.4,
+                                     lambda_=0.5)
+    rot = P.exponential_rotational_slip(top, OMEGA, 41.9, 0.3, 19e-3, VT)
+    return _finish("cfg3", m, _fields(m, seed, "tanh"), sheppard_wright_aa6061(), mix, stick, rot, seed)
+
+
+def cfg4(dims=(256, 256, 256)) -> Case:
+    """fluid region of the two-region case: hex 256^3, NortonHoff, qfric skipped (SURVEY D-1)."""
+    seed = SEED0 + 4
+    m = _hex(dims, 0.25e-3)
+    top = m.patch_id("zmax")
+    mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
+    rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
+    return _finish("cfg4", m, _fields(m, seed, "tanh"), norton_hoff_placeholder(), mix, P.no_friction_patch(0.9), rot,
+                   seed)
+
+
+def cfg5_slab(rank, n_ranks, dims_per_rank=(512, 512, 32)) -> Case:
+    """rank's z-slab of the AFSD box (512x512x256 at 8 ranks), SheppardWright, processor patches."""
+    seed = SEED0 + 5
+    nx, ny, nzr = dims_per_rank
+    cell = 0.25e-3
+    side = [-1] * 6
+    if rank > 0:
+        side[4] = rank - 1
+    if rank < n_ranks - 1:
+        side[5] = rank + 1
+    m = _hex((nx, ny, nzr), cell, side=tuple(side), rank=rank, origin=(0.0, 0.0, rank * nzr * cell))
+    top = m.patch_id("zmax")
+    mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
+    if top >= 0:
+        stick = P.constant_slip_stick(top, betaTQ=0.9, delta=0.5, omega=OMEGA, muf=0.3)
+        rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
+    else:
+        stick = P.no_friction_patch(0.9)
+        rot = None
+    z0 = 0.6 * n_ranks * nzr * cell
+    box = ((0.0, 0.0, 0.0), (nx * cell, ny * cell, n_ranks * nzr * cell))
+    return _finish("cfg5", m, _fields(m, seed + rank, "tanh", z0=z0, box=box), sheppard_wright_aa6061(), mix, stick,
+                   rot, seed,
+                   meta=dict(rank=rank, n_ranks=n_ranks))
+
+
+def advance(case: Case, step: int) -> None:
+    """cfg1's '10 updates with U,T advanced analytically per step' (SURVEY §8d)."""
+    flds = _fields(case.mesh, case.meta["seed"], "step" if case.name == "cfg1" else "tanh", step=step)
+    case.U_i, case.U_b, case.T_i, case.T_b = flds[0], flds[1], flds[2], flds[3]
+    for pid in range(case.mesh.nPatches):
+        if case.patch_u_bc[pid] == P.BC_ZERO_GRADIENT and case.mesh.patchKind[pid] == P.PATCH_GENERIC:
+            case.U_b[case.mesh.patch_slice_b(pid)] = case.U_i[case.mesh.face_cells(pid)]

@@ -1,0 +1,118 @@
+// Per-element arithmetic of the hot path, written once and used by the staged kernels, the fused
+// kernel and the boundary-face kernel, so "fused == staged" holds by construction.
+//
+// Every expression keeps the reference's operator order (C++ left-to-right; one rounded FP64
+// operation per operator).  The translation unit is compiled with -fmad=false, so nvcc never
+// contracts a*b+c into an FMA here -- OpenFOAM's stock gcc build has none.
+// Division and sqrt are IEEE round-to-nearest in CUDA FP64, so everything except exp/log/pow/
+// asinh is bit-identical to the host.
+#pragma once
+#include <cstdint>
+
+#include "ssam_gpu.h"
+
+namespace ssam {
+
+#define SSAM_DEV __device__ __forceinline__
+
+constexpr double kSMALL = 1e-15;    // Foam::SMALL
+constexpr double kVSMALL = 1e-300;  // Foam::VSMALL
+
+// Foam::max / Foam::min: (a > b) ? a : b and (a < b) ? a : b, argument order as written
+// (fmax/fmin differ for NaN)
+SSAM_DEV double ofMax(double a, double b) { return (a > b) ? a : b; }
+SSAM_DEV double ofMin(double a, double b) { return (a < b) ? a : b; }
+
+// x/x evaluated without a divide: exactly 1 for finite non-zero x, NaN for 0, +-inf, NaN --
+// bit-identical to the IEEE quotient the reference computes in k0*(T/T) and k*(T/T)
+// (incompressibleTwoPhaseThermalMixture.C:253,269).
+SSAM_DEV double selfRatio(double x) {
+    const bool ok = (x == x) && (x != 0.0) && (fabs(x) != __longlong_as_double(0x7ff0000000000000LL));
+    return ok ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+// ---- tensor algebra (OpenFOAM SymmTensorI.H) -------------------------------------
+// mag(symm(T)) with T row-major xx,xy,xz,yx,yy,yz,zx,zy,zz
+SSAM_DEV double magSymm(const double (&g)[9]) {
+    const double xx = g[0], xy = 0.5 * (g[1] + g[3]), xz = 0.5 * (g[2] + g[6]);
+    const double yy = g[4], yz = 0.5 * (g[5] + g[7]), zz = g[8];
+    const double ms = xx * xx + 2 * (xy * xy) + 2 * (xz * xz) + yy * yy + 2 * (yz * yz) + zz * zz;
+    return sqrt(ms);
+}
+SSAM_DEV double magVec(double x, double y, double z) { return sqrt(x * x + y * y + z * z); }
+
+// ---- viscosity models --------------------------------------------------------------------------------
+struct ViscOut {
+    double nu, sigmaf, sigmay;
+};
+
+// SheppardWright.C:51-118; correct() SheppardWright.H:133-138
+SSAM_DEV ViscOut sheppardWright(const ssam_viscosity_params& p, double T, double e) {
+    ViscOut o;
+    const double ex = exp(p.Q / (p.R * T));  // shared by Z() (:64) and sigmay() (:91): same bits
+    const double Z = e * ex;
+    const double rn = 1 / p.n;
+    o.sigmaf = p.sigmaR * asinh(pow(Z / p.A, rn));           // :74
+    o.sigmay = p.sigmaR * asinh(pow((0.1 * ex) / p.A, rn));  // :91
+    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, o.sigmaf / ((3.0 * p.rho) * ofMax(e, p.eDotMin))));  // :109-117
+    return o;
+}
+
+// FKS.C:63-183; correct() FKS.H:156-161
+SSAM_DEV ViscOut fks(const ssam_viscosity_params& p, double T, double e) {
+    ViscOut o;
+    const double Tlim = ofMin(ofMax(T, p.Ta), p.Tm);                       // :108
+    const double Th = (Tlim - p.Ta) / (p.Tm - p.Ta);                       // :112
+    const double H = ((p.a1 + (p.a2 * 1.571)) * T) / T;                    // :73
+    const double pw = p.b1 * pow(Th + kSMALL, p.b2);                       // :89 / :152
+    const double Lam = 1.0 + pw * (p.b3 * log(e / p.e0 + kVSMALL));        // :89
+    const double Theta = 1.0 - 1.0 / pow(1.0 + exp((-p.c1) * Th), 1 / p.c2);  // :99
+    o.sigmaf = (H * Lam) * Theta;                                           // :129
+    o.sigmay = (p.a1 * Theta) * (1.0 + pw * (p.b3 * log(0.1 / p.e0 + kVSMALL)));  // :152
+    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, o.sigmaf / ((3.0 * p.rho) * ofMax(e, p.eDotMin))));  // :172-181
+    return o;
+}
+
+// NortonHoff.C:53-66, sr = viscosityModel::strainRate() = sqrt(2)*mag(symm(grad U))
+SSAM_DEV double nortonHoff(const ssam_viscosity_params& p, double sr) {
+    return ofMax(p.nuMin,
+                 ofMin(p.nuMax, (p.mu0 / p.rho) * pow((sqrt(3.0) * ofMax(sr, p.strainRateEffMin)) / 1.0, p.m - 1)));
+}
+
+// ---- mixture (incompressibleTwoPhaseThermalMixture.C) ----------------------------------------------
+SSAM_DEV double limitedAlpha(double a) { return ofMin(ofMax(a, 0.0), 1.0); }  // :49,:138
+
+SSAM_DEV double mixMu(const ssam_mixture_params& p, double la, double nu1, double nu2) {  // :149-150
+    return ((la * la) * p.rho1) * nu1 + (((1.0 - la) * (1.0 - la)) * p.rho2) * nu2;
+}
+SSAM_DEV double mixLinear(double la, double v1, double v2) { return la * v1 + (1.0 - la) * v2; }  // :359,:378,:397
+
+// k1()/k2() :205-343.  shift = 0 (Kelvin) or -273.0 (Celsius), resolved on the host.
+SSAM_DEV double phaseK(const ssam_conductivity& k, double shift, double T) {
+    if (k.kModel == SSAM_K_CUBIC) {
+        const double Tl = ofMin(ofMax(T + shift, k.Tmin), k.Tmax);  // :244
+        // :253  k0*(Tl/Tl) + k1*Tl + k2*pow(Tl,2) + k3*pow(Tl,3); pow(x,2|3) as products: glibc's pow
+        // differs from the correctly rounded product by <= 1 ulp (inside the 1e-11 gate)
+        return k.k0 * selfRatio(Tl) + k.k1 * Tl + k.k2 * (Tl * Tl) + k.k3 * ((Tl * Tl) * Tl);
+    }
+    return k.k * selfRatio(T);  // :269
+}
+
+// ---- friction (constantSlipStick.C / exponentialSlipStick.C) ---------------------------------------
+SSAM_DEV double qviscOf(double betaTQ, double mu, double e) { return ((3.0 * betaTQ) * mu) * (e * e); }  // :58
+
+// qfric at a friction cell (fricCell_ = 1): constantSlipStick.C:100, exponentialSlipStick.C:100,156,164
+SSAM_DEV double qfricOf(const ssam_stick_params& p, double magOmega, double alpha, double sigmay, double pr,
+                        double magR) {
+    double inner;
+    if (p.model == SSAM_STICK_CONSTANT) {
+        inner = (((1.0 - p.delta) * p.betaTQ) * sigmay) / sqrt(3.0) + (p.delta * p.muf) * pr;
+    } else {
+        const double d = 1.0 - exp(((-magOmega) * magR) / ((p.delta0 * p.omega0) * p.Rs));
+        const double mf = p.mu0 * exp((((-p.lambda) * d) * magOmega) * magR);
+        inner = (((1.0 - d) * p.betaTQ) * sigmay) / sqrt(3.0) + (d * mf) * pr;
+    }
+    return ((1.0 * alpha) * inner) * (magOmega * magR);
+}
+
+}  // namespace ssam

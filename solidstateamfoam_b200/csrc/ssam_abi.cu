@@ -1,0 +1,1076 @@
+// C-ABI of the B200-native constitutive + heat-source update (include/ssam_gpu.h).
+// Host-side orchestration only: every number is produced by the kernels in kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+#include "ssam_gpu.h"
+
+using namespace ssam;
+
+struct ssam_ctx {
+    int device = 0;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    bool blocking = true;
+    std::string err;
+    int64_t launches = 0;
+
+    int nCells = 0, nIF = 0, nFaces = 0, nBnd = 0, nTot = 0, nPatches = 0;
+    bool haveMesh = false;
+    std::vector<int> patchStart, patchSize, patchKind, patchNbrRank, patchUbc;
+    std::vector<unsigned char> bndFlagsHost;
+
+    FaceGeo* geo = nullptr;
+    int *owner = nullptr, *neighbour = nullptr, *ownerStart = nullptr, *extraStart = nullptr;
+    int2* extra = nullptr;
+    int nExtra = 0;
+    double *V = nullptr, *magSf_b = nullptr, *deltaCoeffs_b = nullptr;
+    double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
+    unsigned char* bndFlags = nullptr;
+    double* gradB[9] = {nullptr};
+
+    double* plane[SSAM_F_COUNT][9] = {{nullptr}};
+    bool isSet[SSAM_F_COUNT] = {false};
+
+    double* stage = nullptr;
+    size_t stageCap = 0;
+
+    int fricPatchCached = -1;
+    double* fricSums = nullptr;  // device: [0..3] local sums, [4..7] cross-rank sums
+    int qfricZeroedFor = -2;
+
+    // halo
+    int nProcPatches = 0, nProcFaces = 0;
+    std::vector<int> haloPatch;    // patch index of each processor patch
+    std::vector<int> haloOffsets;  // offsets into the send-cell list
+    int* haloSendCells = nullptr;
+    double* sendBuf = nullptr;
+    size_t sendCap = 0;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nRanks = 1;
+
+    // lazily built integer tables
+    int *cellFacesStart = nullptr, *cellFaces = nullptr, *faceColour = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_globalErr;
+
+int ncompOf(int f) { return f == SSAM_F_U ? 3 : (f == SSAM_F_GRADU ? 9 : 1); }
+
+ssam_status fail(ssam_ctx* c, ssam_status st, const std::string& msg) {
+    if (c)
+        c->err = msg;
+    else
+        g_globalErr = msg;
+    return st;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, SSAM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+#define CHECK(cond, st, msg) \
+    do {                     \
+        if (!(cond)) return fail(ctx, st, msg); \
+    } while (0)
+#define TRY(call)                 \
+    do {                          \
+        ssam_status s_ = (call);  \
+        if (s_ != SSAM_OK) return s_; \
+    } while (0)
+#define NC(call)                                                                                              \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess)                                                                                \
+            return fail(ctx, SSAM_ERR_COMM, std::string(#call) + ": " + nccl().GetErrorString(r_));          \
+    } while (0)
+
+inline int gridFor(long long n, int block) { return int((n + block - 1) / block); }
+
+// launch + count + error check
+#define LAUNCH(kernel, grid, block, ...)                                                  \
+    do {                                                                                  \
+        if ((grid) > 0) {                                                                 \
+            kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                     \
+            ctx->launches++;                                                              \
+            CU(cudaGetLastError());                                                       \
+        }                                                                                 \
+    } while (0)
+
+ssam_status finish(ssam_ctx* ctx) {
+    if (ctx->blocking) CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+template <class T>
+ssam_status devAlloc(ssam_ctx* ctx, T** p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CU(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+    return SSAM_OK;
+}
+template <class T>
+void devFree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+ssam_status ensureStage(ssam_ctx* ctx, size_t nDoubles) {
+    if (ctx->stageCap >= nDoubles) return SSAM_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    devFree(ctx->stage);
+    TRY(devAlloc(ctx, &ctx->stage, nDoubles));
+    ctx->stageCap = nDoubles;
+    return SSAM_OK;
+}
+
+ssam_status ensureField(ssam_ctx* ctx, int f) {
+    CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    CHECK(f >= 0 && f < SSAM_F_COUNT, SSAM_ERR_INVALID, "bad field id");
+    const int nc = ncompOf(f);
+    for (int k = 0; k < nc; ++k) {
+        if (ctx->plane[f][k]) continue;
+        TRY(devAlloc(ctx, &ctx->plane[f][k], size_t(ctx->nTot) + 2));
+        CU(cudaMemsetAsync(ctx->plane[f][k], 0, (size_t(ctx->nTot) + 2) * sizeof(double), ctx->stream));
+    }
+    return SSAM_OK;
+}
+
+void freeMesh(ssam_ctx* c) {
+    devFree(c->geo);
+    devFree(c->owner);
+    devFree(c->neighbour);
+    devFree(c->ownerStart);
+    devFree(c->extraStart);
+    devFree(c->extra);
+    devFree(c->V);
+    devFree(c->magSf_b);
+    devFree(c->deltaCoeffs_b);
+    for (auto& p : c->Cpl) devFree(p);
+    devFree(c->bndFlags);
+    for (auto& p : c->gradB) devFree(p);
+    for (int f = 0; f < SSAM_F_COUNT; ++f) {
+        for (auto& p : c->plane[f]) devFree(p);
+        c->isSet[f] = false;
+    }
+    devFree(c->haloSendCells);
+    devFree(c->sendBuf);
+    c->sendCap = 0;
+    devFree(c->cellFacesStart);
+    devFree(c->cellFaces);
+    devFree(c->faceColour);
+    c->fricPatchCached = -1;
+    c->qfricZeroedFor = -2;
+    c->haveMesh = false;
+}
+
+// in-place exclusive scan of n ints on the device
+ssam_status exclusiveScan(ssam_ctx* ctx, int* data, int n) {
+    const int tiles = gridFor(n, SCAN_TILE);
+    if (tiles <= 1) {
+        LAUNCH(k_scan_tile, 1, SCAN_THREADS, data, n, (int*)nullptr);
+        return SSAM_OK;
+    }
+    int* sums = nullptr;
+    TRY(devAlloc(ctx, &sums, size_t(tiles)));
+    LAUNCH(k_scan_tile, tiles, SCAN_THREADS, data, n, sums);
+    ssam_status st = exclusiveScan(ctx, sums, tiles);
+    if (st == SSAM_OK) {
+        k_scan_add<<<gridFor(n, 256), 256, 0, ctx->stream>>>(data, n, sums);
+        ctx->launches++;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(sums);
+    return st;
+}
+
+void rebuildBndFlags(ssam_ctx* c) {
+    c->bndFlagsHost.assign(size_t(std::max(c->nBnd, 1)), 0);
+    for (int p = 0; p < c->nPatches; ++p) {
+        unsigned char fl = 0;
+        if (c->patchKind[p] == SSAM_PATCH_PROCESSOR)
+            fl |= BND_COUPLED;
+        else if (c->patchUbc[p] == SSAM_BC_ZERO_GRADIENT)
+            fl |= BND_ZERO_GRADIENT;
+        for (int f = c->patchStart[p]; f < c->patchStart[p] + c->patchSize[p]; ++f) c->bndFlagsHost[f - c->nIF] = fl;
+    }
+}
+
+ssam_status buildAddressing(ssam_ctx* ctx) {
+    const int nc = ctx->nCells, nIF = ctx->nIF, nF = ctx->nFaces;
+    TRY(devAlloc(ctx, &ctx->ownerStart, size_t(nc) + 1));
+    TRY(devAlloc(ctx, &ctx->extraStart, size_t(nc) + 1));
+    int* errFlag = nullptr;
+    TRY(devAlloc(ctx, &errFlag, 1));
+    CU(cudaMemsetAsync(errFlag, 0, sizeof(int), ctx->stream));
+    LAUNCH(k_owner_start, gridFor(nIF + 1, 256), 256, ctx->owner, nIF, nc, ctx->ownerStart, errFlag);
+    int herr = 0;
+    CU(cudaMemcpyAsync(&herr, errFlag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(errFlag);
+    CHECK(herr == 0, SSAM_ERR_INVALID,
+          "owner[] of the internal faces is not ascending: the mesh is not in upper-triangular order");
+    CU(cudaMemsetAsync(ctx->extraStart, 0, (size_t(nc) + 1) * sizeof(int), ctx->stream));
+    LAUNCH(k_extra_count, gridFor(nF, 256), 256, ctx->owner, ctx->neighbour, nIF, nF, ctx->extraStart);
+    TRY(exclusiveScan(ctx, ctx->extraStart, nc + 1));
+    ctx->nExtra = nIF + ctx->nBnd;
+    TRY(devAlloc(ctx, &ctx->extra, size_t(ctx->nExtra)));
+    int* cursor = nullptr;
+    TRY(devAlloc(ctx, &cursor, size_t(nc) + 1));
+    CU(cudaMemcpyAsync(cursor, ctx->extraStart, (size_t(nc) + 1) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    LAUNCH(k_extra_fill, gridFor(nF, 256), 256, ctx->owner, ctx->neighbour, ctx->bndFlags, nIF, nF, cursor, ctx->extra);
+    LAUNCH(k_extra_sort, gridFor(nc, 256), 256, ctx->extraStart, nc, ctx->extra);
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(cursor);
+    return SSAM_OK;
+}
+
+ssam_status uploadAoS(ssam_ctx* ctx, const double* host, int n, int nc, double* const* planes, int offset) {
+    if (n == 0) return SSAM_OK;
+    if (nc == 1) {
+        CU(cudaMemcpyAsync(planes[0] + offset, host, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        return SSAM_OK;
+    }
+    TRY(ensureStage(ctx, size_t(n) * nc));
+    CU(cudaMemcpyAsync(ctx->stage, host, size_t(n) * nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PlanePtrs pl;
+    for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
+    LAUNCH(k_aos_to_soa_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset);
+    return SSAM_OK;
+}
+
+ssam_status downloadAoS(ssam_ctx* ctx, double* host, int n, int nc, double* const* planes, int offset) {
+    if (n == 0) return SSAM_OK;
+    if (nc == 1) {
+        CU(cudaMemcpyAsync(host, planes[0] + offset, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        return SSAM_OK;
+    }
+    TRY(ensureStage(ctx, size_t(n) * nc));
+    PlanePtrs pl;
+    for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
+    LAUNCH(k_soa_to_aos_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset);
+    CU(cudaMemcpyAsync(host, ctx->stage, size_t(n) * nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    // the staging buffer is reused by the next transfer
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+ssam_status need(ssam_ctx* ctx, int f, const char* what) {
+    CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    if (!ctx->isSet[f]) return fail(ctx, SSAM_ERR_MISSING_FIELD, std::string("field not available: ") + what);
+    return SSAM_OK;
+}
+
+ssam_status unitsShift(ssam_ctx* ctx, const ssam_conductivity& k, double* shift) {
+    *shift = 0.0;
+    if (k.kModel != SSAM_K_CUBIC) return SSAM_OK;
+    *shift = -273.0;  // celsConv_, incompressibleTwoPhaseThermalMixture.C:226
+    if (k.units == SSAM_UNITS_KELVIN)
+        *shift = 0.0;
+    else if (k.units != SSAM_UNITS_CELSIUS)
+        return fail(ctx, SSAM_ERR_UNITS, "Unknown conductivity function units. Choose Kelvin or Celsius.");
+    return SSAM_OK;
+}
+
+ssam_status checkViscModel(ssam_ctx* ctx, const ssam_viscosity_params* p) {
+    CHECK(p != nullptr, SSAM_ERR_INVALID, "null viscosity params");
+    CHECK(p->model >= SSAM_VISC_NEWTONIAN && p->model <= SSAM_VISC_NORTON_HOFF, SSAM_ERR_UNKNOWN_MODEL,
+          "Unknown viscosityModel type");
+    return SSAM_OK;
+}
+
+void fillMeshArgs(ssam_ctx* c, UpdateArgs& a) {
+    std::memset(&a, 0, sizeof(a));
+    a.nCells = c->nCells;
+    a.nIF = c->nIF;
+    a.nBnd = c->nBnd;
+    a.geo = c->geo;
+    a.owner = c->owner;
+    a.neighbour = c->neighbour;
+    a.ownerStart = c->ownerStart;
+    a.extraStart = c->extraStart;
+    a.extra = c->extra;
+    a.V = c->V;
+    a.magSf_b = c->magSf_b;
+    a.deltaCoeffs_b = c->deltaCoeffs_b;
+    a.bndFlags = c->bndFlags;
+    a.Ux = c->plane[SSAM_F_U][0];
+    a.Uy = c->plane[SSAM_F_U][1];
+    a.Uz = c->plane[SSAM_F_U][2];
+    for (int k = 0; k < 9; ++k) a.gradB[k] = c->gradB[k];
+    a.epsFactor = std::sqrt(2.0 / 3.0);  // Foam::sqrt(2.0/3.0), fluid/TEqn.H:3
+    a.srFactor = std::sqrt(2.0);         // viscosityModel::strainRate()
+}
+
+// ---- halo exchange --------------------------------------------------------------------------------------
+ssam_status haloExchangeField(ssam_ctx* ctx, int field) {
+    if (ctx->nProcPatches == 0) return SSAM_OK;
+    CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
+    TRY(ensureField(ctx, field));
+    const int nc = ncompOf(field);
+    const size_t needBuf = size_t(ctx->nProcFaces) * nc;
+    if (ctx->sendCap < needBuf) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        devFree(ctx->sendBuf);
+        TRY(devAlloc(ctx, &ctx->sendBuf, needBuf));
+        ctx->sendCap = needBuf;
+    }
+    HaloLayout L;
+    L.nPatches = ctx->nProcPatches;
+    for (int p = 0; p <= ctx->nProcPatches; ++p) L.offsets[p] = ctx->haloOffsets[p];
+    PlanePtrs pl;
+    for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? ctx->plane[field][k] : nullptr;
+    LAUNCH(k_halo_pack, gridFor((long long)ctx->nProcFaces * nc, 256), 256, ctx->haloSendCells, L, nc, pl, ctx->sendBuf);
+    NcclApi& N = nccl();
+    NC(N.GroupStart());
+    for (int p = 0; p < ctx->nProcPatches; ++p) {
+        const int patch = ctx->haloPatch[p];
+        const int peer = ctx->patchNbrRank[patch];
+        const int off = ctx->haloOffsets[p], np = ctx->haloOffsets[p + 1] - off;
+        const int b0 = ctx->patchStart[patch] - ctx->nIF;
+        for (int k = 0; k < nc; ++k) {
+            NC(N.Send(ctx->sendBuf + size_t(nc) * off + size_t(k) * np, np, ncclFloat64, peer, ctx->comm, ctx->stream));
+            NC(N.Recv(ctx->plane[field][k] + ctx->nCells + b0, np, ncclFloat64, peer, ctx->comm, ctx->stream));
+        }
+    }
+    NC(N.GroupEnd());
+    ctx->launches++;  // one fused NCCL p2p kernel per group
+    return SSAM_OK;
+}
+
+ssam_status ensureFricSums(ssam_ctx* ctx, int patch) {
+    if (ctx->fricPatchCached == patch) return SSAM_OK;
+    if (!ctx->fricSums) TRY(devAlloc(ctx, &ctx->fricSums, 8));
+    const int b0 = ctx->patchStart[patch] - ctx->nIF;
+    LAUNCH(k_patch_sums, 1, 32, b0, ctx->patchSize[patch], ctx->Cpl[0], ctx->Cpl[1], ctx->Cpl[2], ctx->magSf_b,
+           ctx->nCells, ctx->fricSums);
+    if (ctx->comm && ctx->nRanks > 1) {
+        // reduce(patchCenter_, sumOp<vector>()); reduce(patchArea_, sumOp<scalar>())  (constantSlipStick.C:134-135)
+        // NB every rank starts its area at VSMALL like the reference does.
+        NC(nccl().AllReduce(ctx->fricSums, ctx->fricSums + 4, 4, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+        ctx->launches++;
+    } else {
+        CU(cudaMemcpyAsync(ctx->fricSums + 4, ctx->fricSums, 4 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    ctx->fricPatchCached = patch;
+    return SSAM_OK;
+}
+
+ssam_status launchQfric(ssam_ctx* ctx, const ssam_stick_params& p) {
+    CHECK(p.fricPatch < ctx->nPatches, SSAM_ERR_INVALID, "fricPatch out of range (findPatchID returned -1?)");
+    CHECK(p.model == SSAM_STICK_CONSTANT || p.model == SSAM_STICK_EXPONENTIAL, SSAM_ERR_UNKNOWN_MODEL,
+          "Unknown stickModel type");
+    TRY(need(ctx, SSAM_F_SIGMAY, "sigmay (NortonHoff registers none, SURVEY D-1)"));
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(need(ctx, SSAM_F_P, "p"));
+    TRY(ensureField(ctx, SSAM_F_QFRIC));
+    if (ctx->qfricZeroedFor != p.fricPatch) {
+        // fricCell_ = alpha_*0.0 everywhere except the patch cells (:79-92): zero-filled once per patch
+        CU(cudaMemsetAsync(ctx->plane[SSAM_F_QFRIC][0], 0, size_t(ctx->nTot) * sizeof(double), ctx->stream));
+        ctx->qfricZeroedFor = p.fricPatch;
+    }
+    TRY(ensureFricSums(ctx, p.fricPatch));
+    const int n = ctx->patchSize[p.fricPatch];
+    LAUNCH(k_qfric, gridFor(n, 128), 128, p, ctx->patchStart[p.fricPatch], n, ctx->owner, ctx->Cpl[0], ctx->Cpl[1],
+           ctx->Cpl[2], ctx->fricSums + 4, ctx->plane[SSAM_F_ALPHA1][0], ctx->plane[SSAM_F_SIGMAY][0],
+           ctx->plane[SSAM_F_P][0], ctx->plane[SSAM_F_QFRIC][0]);
+    ctx->isSet[SSAM_F_QFRIC] = true;
+    return SSAM_OK;
+}
+
+template <int MODE>
+ssam_status launchCellsBoundary(ssam_ctx* ctx, const UpdateArgs& a, int model1, bool boundaryToo) {
+    const int gc = gridFor(ctx->nCells, 256), gb = gridFor(ctx->nBnd, 128);
+#define SSAM_DISPATCH(M)                                                    \
+    case M:                                                                 \
+        if (!boundaryToo) {                                                 \
+            LAUNCH((k_cells<M, MODE>), gc, 256, a);                         \
+        } else {                                                            \
+            LAUNCH((k_boundary<M, MODE>), gb, 128, a);                      \
+        }                                                                   \
+        break;
+    switch (model1) {
+        SSAM_DISPATCH(SSAM_VISC_NEWTONIAN)
+        SSAM_DISPATCH(SSAM_VISC_SHEPPARD_WRIGHT)
+        SSAM_DISPATCH(SSAM_VISC_FKS)
+        SSAM_DISPATCH(SSAM_VISC_NORTON_HOFF)
+        default:
+            return fail(ctx, SSAM_ERR_UNKNOWN_MODEL, "Unknown viscosityModel type");
+    }
+#undef SSAM_DISPATCH
+    return SSAM_OK;
+}
+
+// fvc::grad(U) pieces: MODE_GRAD writes GRADU, MODE_STRAIN writes factor*mag(symm(grad U)) into outField
+ssam_status gradOrStrain(ssam_ctx* ctx, bool strain, double factor, int outField) {
+    TRY(need(ctx, SSAM_F_U, "U"));
+    UpdateArgs a;
+    fillMeshArgs(ctx, a);
+    if (strain) {
+        TRY(ensureField(ctx, outField));
+        a.strainOut = ctx->plane[outField][0];
+        a.strainFactor = factor;
+        TRY((launchCellsBoundary<MODE_STRAIN>(ctx, a, SSAM_VISC_NEWTONIAN, false)));
+        if (ctx->nProcPatches) TRY(haloExchangeField(ctx, outField));
+        TRY((launchCellsBoundary<MODE_STRAIN>(ctx, a, SSAM_VISC_NEWTONIAN, true)));
+        ctx->isSet[outField] = true;
+    } else {
+        TRY(ensureField(ctx, SSAM_F_GRADU));
+        for (int k = 0; k < 9; ++k) a.gradU[k] = ctx->plane[SSAM_F_GRADU][k];
+        TRY((launchCellsBoundary<MODE_GRAD>(ctx, a, SSAM_VISC_NEWTONIAN, false)));
+        if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_GRADU));
+        TRY((launchCellsBoundary<MODE_GRAD>(ctx, a, SSAM_VISC_NEWTONIAN, true)));
+        ctx->isSet[SSAM_F_GRADU] = true;
+    }
+    return SSAM_OK;
+}
+
+ssam_status viscosityCorrect(ssam_ctx* ctx, int phase, const ssam_viscosity_params* p) {
+    CHECK(phase == 1 || phase == 2, SSAM_ERR_INVALID, "phase must be 1 or 2");
+    TRY(checkViscModel(ctx, p));
+    const int nuField = phase == 1 ? SSAM_F_NU1 : SSAM_F_NU2;
+    TRY(ensureField(ctx, nuField));
+    ViscStage s;
+    s.p = *p;
+    s.T = s.eps = s.sr = nullptr;
+    s.sigmaf = s.sigmay = nullptr;
+    s.nu = ctx->plane[nuField][0];
+    if (p->model == SSAM_VISC_SHEPPARD_WRIGHT || p->model == SSAM_VISC_FKS) {
+        TRY(need(ctx, SSAM_F_T, "temp"));
+        TRY(need(ctx, SSAM_F_EPSDOT, "epsilonDotEq"));
+        TRY(ensureField(ctx, SSAM_F_SIGMAF));
+        TRY(ensureField(ctx, SSAM_F_SIGMAY));
+        s.T = ctx->plane[SSAM_F_T][0];
+        s.eps = ctx->plane[SSAM_F_EPSDOT][0];
+        s.sigmaf = ctx->plane[SSAM_F_SIGMAF][0];
+        s.sigmay = ctx->plane[SSAM_F_SIGMAY][0];
+    } else if (p->model == SSAM_VISC_NORTON_HOFF) {
+        // calcNu() calls strainRate() = sqrt(2)*mag(symm(fvc::grad(U_)))  (NortonHoff.C:62)
+        TRY(gradOrStrain(ctx, true, std::sqrt(2.0), SSAM_F_STRAINRATE));
+        s.sr = ctx->plane[SSAM_F_STRAINRATE][0];
+    }
+    LAUNCH((k_map<ViscStage>), std::min(gridFor(ctx->nTot, 256), 148 * 32), 256, ctx->nTot, s);
+    ctx->isSet[nuField] = true;
+    if (s.sigmaf) ctx->isSet[SSAM_F_SIGMAF] = ctx->isSet[SSAM_F_SIGMAY] = true;
+    return SSAM_OK;
+}
+
+int mapGrid(const ssam_ctx* c) { return std::min(gridFor(c->nTot, 256), 148 * 32); }
+
+ssam_status mixtureCalcNu(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(need(ctx, SSAM_F_NU1, "nu1"));
+    TRY(need(ctx, SSAM_F_NU2, "nu2"));
+    TRY(ensureField(ctx, SSAM_F_NU));
+    CalcNuStage s{*p, ctx->plane[SSAM_F_ALPHA1][0], ctx->plane[SSAM_F_NU1][0], ctx->plane[SSAM_F_NU2][0],
+                  ctx->plane[SSAM_F_NU][0]};
+    LAUNCH((k_map<CalcNuStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    ctx->isSet[SSAM_F_NU] = true;
+    return SSAM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int ssam_abi_version(void) { return 1; }
+
+ssam_status ssam_create(ssam_ctx** out, int device) {
+    ssam_ctx* ctx = nullptr;
+    CHECK(out != nullptr, SSAM_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SSAM_ERR_CUDA,
+                    std::string("no CUDA device (this path has no CPU fallback): ") + cudaGetErrorString(e));
+    CHECK(device >= 0 && device < count, SSAM_ERR_INVALID, "device out of range");
+    CU(cudaSetDevice(device));
+    ssam_ctx* c = new ssam_ctx;
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, SSAM_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    c->stream = c->ownStream;
+    *out = c;
+    return SSAM_OK;
+}
+
+ssam_status ssam_destroy(ssam_ctx* ctx) {
+    if (!ctx) return SSAM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) nccl().CommDestroy(ctx->comm);
+    freeMesh(ctx);
+    devFree(ctx->stage);
+    devFree(ctx->fricSums);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+    return SSAM_OK;
+}
+
+const char* ssam_last_error(const ssam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_globalErr.c_str(); }
+
+ssam_status ssam_sync(ssam_ctx* ctx) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+ssam_status ssam_set_stream(ssam_ctx* ctx, void* s) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->ownStream;
+    return SSAM_OK;
+}
+
+ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    ctx->blocking = blocking != 0;
+    return SSAM_OK;
+}
+
+int64_t ssam_launch_count(const ssam_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- mesh -------------------------------------------------------------------------------------------
+ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
+    CHECK(ctx && m, SSAM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    CHECK(m->nCells > 0 && m->nInternalFaces >= 0 && m->nFaces >= m->nInternalFaces && m->nPatches >= 0,
+          SSAM_ERR_INVALID, "bad mesh sizes");
+    CHECK(m->owner && m->Sf && m->weights && m->V && m->C && m->patchStart && m->patchSize && m->patchKind &&
+              m->patchNbrRank,
+          SSAM_ERR_INVALID, "null mesh array");
+    CU(cudaStreamSynchronize(ctx->stream));
+    freeMesh(ctx);
+    ctx->nCells = m->nCells;
+    ctx->nIF = m->nInternalFaces;
+    ctx->nFaces = m->nFaces;
+    ctx->nBnd = m->nFaces - m->nInternalFaces;
+    ctx->nTot = ctx->nCells + ctx->nBnd;
+    ctx->nPatches = m->nPatches;
+    ctx->patchStart.assign(m->patchStart, m->patchStart + m->nPatches);
+    ctx->patchSize.assign(m->patchSize, m->patchSize + m->nPatches);
+    ctx->patchKind.assign(m->patchKind, m->patchKind + m->nPatches);
+    ctx->patchNbrRank.assign(m->patchNbrRank, m->patchNbrRank + m->nPatches);
+    ctx->patchUbc.assign(m->nPatches, SSAM_BC_VALUE);
+    // patches must tile [nIF, nFaces) in order
+    int expect = ctx->nIF;
+    for (int p = 0; p < m->nPatches; ++p) {
+        CHECK(ctx->patchStart[p] == expect && ctx->patchSize[p] >= 0, SSAM_ERR_INVALID,
+              "patches must be contiguous and ordered after the internal faces");
+        expect += ctx->patchSize[p];
+    }
+    CHECK(expect == ctx->nFaces, SSAM_ERR_INVALID, "patches do not cover the boundary faces");
+    ctx->haveMesh = true;
+
+    const size_t nF = size_t(ctx->nFaces), nC = size_t(ctx->nCells), nB = size_t(ctx->nBnd);
+    TRY(devAlloc(ctx, &ctx->owner, nF));
+    TRY(devAlloc(ctx, &ctx->neighbour, size_t(ctx->nIF)));
+    CU(cudaMemcpyAsync(ctx->owner, m->owner, nF * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->nIF)
+        CU(cudaMemcpyAsync(ctx->neighbour, m->neighbour, size_t(ctx->nIF) * sizeof(int), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    // {Sf, w} -> one 32-byte record per face
+    TRY(devAlloc(ctx, &ctx->geo, nF));
+    {
+        double *dSf = nullptr, *dW = nullptr;
+        TRY(devAlloc(ctx, &dSf, 3 * nF));
+        TRY(devAlloc(ctx, &dW, nF));
+        CU(cudaMemcpyAsync(dSf, m->Sf, 3 * nF * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dW, m->weights, nF * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_pack_geo, gridFor((long long)nF, 256), 256, dSf, dW, ctx->nFaces, ctx->geo);
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(dSf);
+        cudaFree(dW);
+    }
+    TRY(devAlloc(ctx, &ctx->V, nC));
+    CU(cudaMemcpyAsync(ctx->V, m->V, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(devAlloc(ctx, &ctx->magSf_b, nB));
+    TRY(devAlloc(ctx, &ctx->deltaCoeffs_b, nB));
+    if (nB) {
+        CHECK(m->Cf_b && m->magSf_b && m->deltaCoeffs_b, SSAM_ERR_INVALID, "null boundary geometry");
+        CU(cudaMemcpyAsync(ctx->magSf_b, m->magSf_b, nB * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->deltaCoeffs_b, m->deltaCoeffs_b, nB * sizeof(double), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    }
+    for (int k = 0; k < 3; ++k) TRY(devAlloc(ctx, &ctx->Cpl[k], size_t(ctx->nTot) + 2));
+    TRY(uploadAoS(ctx, m->C, ctx->nCells, 3, ctx->Cpl, 0));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (nB) TRY(uploadAoS(ctx, m->Cf_b, ctx->nBnd, 3, ctx->Cpl, ctx->nCells));
+    for (int k = 0; k < 9; ++k) TRY(devAlloc(ctx, &ctx->gradB[k], nB));
+    rebuildBndFlags(ctx);
+    TRY(devAlloc(ctx, &ctx->bndFlags, nB));
+    if (nB)
+        CU(cudaMemcpyAsync(ctx->bndFlags, ctx->bndFlagsHost.data(), nB, cudaMemcpyHostToDevice, ctx->stream));
+    // halo maps: faceCells of every processor patch in patch-face order
+    ctx->haloPatch.clear();
+    ctx->haloOffsets.assign(1, 0);
+    for (int p = 0; p < ctx->nPatches; ++p)
+        if (ctx->patchKind[p] == SSAM_PATCH_PROCESSOR) {
+            ctx->haloPatch.push_back(p);
+            ctx->haloOffsets.push_back(ctx->haloOffsets.back() + ctx->patchSize[p]);
+        }
+    ctx->nProcPatches = int(ctx->haloPatch.size());
+    ctx->nProcFaces = ctx->haloOffsets.back();
+    CHECK(ctx->nProcPatches <= 32, SSAM_ERR_INVALID, "more than 32 processor patches on one rank");
+    TRY(devAlloc(ctx, &ctx->haloSendCells, size_t(ctx->nProcFaces)));
+    for (int p = 0; p < ctx->nProcPatches; ++p) {
+        const int patch = ctx->haloPatch[p];
+        CU(cudaMemcpyAsync(ctx->haloSendCells + ctx->haloOffsets[p], ctx->owner + ctx->patchStart[patch],
+                           size_t(ctx->patchSize[patch]) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    TRY(buildAddressing(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+ssam_status ssam_patch_u_bc_set(ssam_ctx* ctx, const int32_t* kinds) {
+    CHECK(ctx && ctx->haveMesh && kinds, SSAM_ERR_INVALID, "mesh not set / null kinds");
+    for (int p = 0; p < ctx->nPatches; ++p) {
+        CHECK(kinds[p] == SSAM_BC_VALUE || kinds[p] == SSAM_BC_ZERO_GRADIENT, SSAM_ERR_INVALID, "bad U bc kind");
+        ctx->patchUbc[p] = kinds[p];
+    }
+    rebuildBndFlags(ctx);
+    if (ctx->nBnd)
+        CU(cudaMemcpyAsync(ctx->bndFlags, ctx->bndFlagsHost.data(), size_t(ctx->nBnd), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+// ---- addressing getters -------------------------------------------------------------------------------
+static ssam_status ensureCellFaces(ssam_ctx* ctx) {
+    if (ctx->cellFaces) return SSAM_OK;
+    TRY(devAlloc(ctx, &ctx->cellFacesStart, size_t(ctx->nCells) + 1));
+    TRY(devAlloc(ctx, &ctx->cellFaces, size_t(2) * ctx->nIF + ctx->nBnd));
+    LAUNCH(k_cell_faces, gridFor(ctx->nCells + 1, 256), 256, ctx->ownerStart, ctx->extraStart, ctx->extra, ctx->nCells,
+           ctx->nIF, ctx->cellFacesStart, ctx->cellFaces);
+    return SSAM_OK;
+}
+
+static ssam_status ensureColouring(ssam_ctx* ctx) {
+    if (ctx->faceColour) return SSAM_OK;
+    TRY(devAlloc(ctx, &ctx->faceColour, size_t(ctx->nIF)));
+    CU(cudaMemsetAsync(ctx->faceColour, 0xff, size_t(ctx->nIF) * sizeof(int), ctx->stream));
+    int* rem = nullptr;
+    TRY(devAlloc(ctx, &rem, 1));
+    for (int sweep = 0; sweep < 1 << 20; ++sweep) {
+        CU(cudaMemsetAsync(rem, 0, sizeof(int), ctx->stream));
+        LAUNCH(k_colour_sweep, gridFor(ctx->nIF, 256), 256, ctx->owner, ctx->neighbour, ctx->ownerStart,
+               ctx->extraStart, ctx->extra, ctx->nIF, ctx->faceColour, rem);
+        int h = 0;
+        CU(cudaMemcpyAsync(&h, rem, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (h == 0) break;
+    }
+    cudaFree(rem);
+    return SSAM_OK;
+}
+
+ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n) {
+    CHECK(ctx && ctx->haveMesh && n, SSAM_ERR_INVALID, "mesh not set");
+    switch (which) {
+        case SSAM_ADDR_OWNER_START:
+        case SSAM_ADDR_EXTRA_START:
+        case SSAM_ADDR_CELL_FACES_START: *n = int64_t(ctx->nCells) + 1; break;
+        case SSAM_ADDR_EXTRA_FACE:
+        case SSAM_ADDR_EXTRA_OTHER: *n = ctx->nExtra; break;
+        case SSAM_ADDR_CELL_FACES: *n = int64_t(2) * ctx->nIF + ctx->nBnd; break;
+        case SSAM_ADDR_HALO_SEND_CELLS: *n = ctx->nProcFaces; break;
+        case SSAM_ADDR_HALO_PATCH_OFFSETS: *n = ctx->nProcPatches + 1; break;
+        case SSAM_ADDR_FRIC_CELLS: *n = ctx->fricPatchCached >= 0 ? ctx->patchSize[ctx->fricPatchCached] : 0; break;
+        case SSAM_ADDR_FACE_COLOUR: *n = ctx->nIF; break;
+        default: return fail(ctx, SSAM_ERR_INVALID, "bad addressing id");
+    }
+    return SSAM_OK;
+}
+
+ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t n) {
+    int64_t have = 0;
+    TRY(ssam_addressing_size(ctx, which, &have));
+    CHECK(out && n == have, SSAM_ERR_INVALID, "size mismatch");
+    if (n == 0) return SSAM_OK;
+    const int* src = nullptr;
+    int* tmp = nullptr;
+    switch (which) {
+        case SSAM_ADDR_OWNER_START: src = ctx->ownerStart; break;
+        case SSAM_ADDR_EXTRA_START: src = ctx->extraStart; break;
+        case SSAM_ADDR_EXTRA_FACE:
+        case SSAM_ADDR_EXTRA_OTHER: {
+            TRY(devAlloc(ctx, &tmp, size_t(2) * n));
+            LAUNCH(k_split_int2, gridFor(n, 256), 256, ctx->extra, int(n), tmp, tmp + n);
+            src = which == SSAM_ADDR_EXTRA_FACE ? tmp : tmp + n;
+            break;
+        }
+        case SSAM_ADDR_CELL_FACES_START:
+            TRY(ensureCellFaces(ctx));
+            src = ctx->cellFacesStart;
+            break;
+        case SSAM_ADDR_CELL_FACES:
+            TRY(ensureCellFaces(ctx));
+            src = ctx->cellFaces;
+            break;
+        case SSAM_ADDR_HALO_SEND_CELLS: src = ctx->haloSendCells; break;
+        case SSAM_ADDR_HALO_PATCH_OFFSETS:
+            std::memcpy(out, ctx->haloOffsets.data(), size_t(n) * sizeof(int));
+            return SSAM_OK;
+        case SSAM_ADDR_FRIC_CELLS: src = ctx->owner + ctx->patchStart[ctx->fricPatchCached]; break;
+        case SSAM_ADDR_FACE_COLOUR:
+            TRY(ensureColouring(ctx));
+            src = ctx->faceColour;
+            break;
+    }
+    CU(cudaMemcpyAsync(out, src, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (tmp) cudaFree(tmp);
+    return SSAM_OK;
+}
+
+// ---- fields -------------------------------------------------------------------------------------------
+ssam_status ssam_field_upload(ssam_ctx* ctx, int field, const double* internal, const double* boundary) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    TRY(ensureField(ctx, field));
+    const int nc = ncompOf(field);
+    if (internal) {
+        TRY(uploadAoS(ctx, internal, ctx->nCells, nc, ctx->plane[field], 0));
+        if (nc > 1) CU(cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+    }
+    if (boundary) TRY(uploadAoS(ctx, boundary, ctx->nBnd, nc, ctx->plane[field], ctx->nCells));
+    ctx->isSet[field] = true;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+ssam_status ssam_field_download(ssam_ctx* ctx, int field, double* internal, double* boundary) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CHECK(field >= 0 && field < SSAM_F_COUNT, SSAM_ERR_INVALID, "bad field id");
+    TRY(need(ctx, field, "download of a field that was never uploaded or computed"));
+    const int nc = ncompOf(field);
+    if (internal) TRY(downloadAoS(ctx, internal, ctx->nCells, nc, ctx->plane[field], 0));
+    if (boundary) TRY(downloadAoS(ctx, boundary, ctx->nBnd, nc, ctx->plane[field], ctx->nCells));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+ssam_status ssam_field_device_ptr(ssam_ctx* ctx, int field, int comp, void** ptr, int64_t* len) {
+    CHECK(ctx && ptr, SSAM_ERR_INVALID, "null argument");
+    TRY(ensureField(ctx, field));
+    CHECK(comp >= 0 && comp < ncompOf(field), SSAM_ERR_INVALID, "bad component");
+    *ptr = ctx->plane[field][comp];
+    if (len) *len = ctx->nTot;
+    ctx->isSet[field] = true;  // the caller fills it on the device
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+int ssam_field_is_set(const ssam_ctx* ctx, int field) {
+    return (ctx && field >= 0 && field < SSAM_F_COUNT && ctx->isSet[field]) ? 1 : 0;
+}
+
+// ---- boundary condition ---------------------------------------------------------------------------------
+ssam_status ssam_bc_rotational_slip(ssam_ctx* ctx, const ssam_rotslip_params* p) {
+    CHECK(ctx && p && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set / null params");
+    CHECK(p->patch >= 0 && p->patch < ctx->nPatches, SSAM_ERR_INVALID, "patch out of range");
+    CHECK(p->model == SSAM_ROTSLIP_CONSTANT || p->model == SSAM_ROTSLIP_EXPONENTIAL, SSAM_ERR_UNKNOWN_MODEL,
+          "Unknown rotational slip patch field type");
+    TRY(ensureField(ctx, SSAM_F_U));
+    const int n = ctx->patchSize[p->patch];
+    LAUNCH(k_bc_rotslip, gridFor(n, 128), 128, *p, ctx->patchStart[p->patch] - ctx->nIF, n, ctx->nCells, ctx->Cpl[0],
+           ctx->Cpl[1], ctx->Cpl[2], ctx->plane[SSAM_F_U][0], ctx->plane[SSAM_F_U][1], ctx->plane[SSAM_F_U][2]);
+    return finish(ctx);
+}
+
+// ---- staged entry points ----------------------------------------------------------------------------------
+ssam_status ssam_grad_u(ssam_ctx* ctx) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    TRY(gradOrStrain(ctx, false, 0.0, SSAM_F_GRADU));
+    return finish(ctx);
+}
+
+ssam_status ssam_strain_rate(ssam_ctx* ctx, double factor, int out_field) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CHECK(out_field == SSAM_F_EPSDOT || out_field == SSAM_F_STRAINRATE, SSAM_ERR_INVALID,
+          "strain rate goes to EPSDOT or STRAINRATE");
+    TRY(gradOrStrain(ctx, true, factor, out_field));
+    return finish(ctx);
+}
+
+ssam_status ssam_viscosity_correct(ssam_ctx* ctx, int phase, const ssam_viscosity_params* p) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    TRY(viscosityCorrect(ctx, phase, p));
+    return finish(ctx);
+}
+
+ssam_status ssam_mixture_calc_nu(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(mixtureCalcNu(ctx, p));
+    return finish(ctx);
+}
+
+ssam_status ssam_thermo_correct(ssam_ctx* ctx, const ssam_viscosity_params* v1, const ssam_viscosity_params* v2,
+                                const ssam_mixture_params* mix) {
+    CHECK(ctx && mix, SSAM_ERR_INVALID, "null argument");
+    TRY(viscosityCorrect(ctx, 1, v1));  // nuModel1_->correct()   (...Mixture.C:43)
+    TRY(viscosityCorrect(ctx, 2, v2));  // nuModel2_->correct()   (:44)
+    TRY(mixtureCalcNu(ctx, mix));       // :46-53
+    return finish(ctx);
+}
+
+ssam_status ssam_mixture_mu(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(need(ctx, SSAM_F_NU1, "nu1"));
+    TRY(need(ctx, SSAM_F_NU2, "nu2"));
+    TRY(ensureField(ctx, SSAM_F_MUEFF));
+    MuStage s{*p, ctx->plane[SSAM_F_ALPHA1][0], ctx->plane[SSAM_F_NU1][0], ctx->plane[SSAM_F_NU2][0],
+              ctx->plane[SSAM_F_MUEFF][0]};
+    LAUNCH((k_map<MuStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    ctx->isSet[SSAM_F_MUEFF] = true;
+    return finish(ctx);
+}
+
+static ssam_status mixtureLinear(ssam_ctx* ctx, int outField, double v1, double v2) {
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(ensureField(ctx, outField));
+    LinearStage s{v1, v2, ctx->plane[SSAM_F_ALPHA1][0], ctx->plane[outField][0]};
+    LAUNCH((k_map<LinearStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    ctx->isSet[outField] = true;
+    return finish(ctx);
+}
+
+ssam_status ssam_mixture_rho(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    return mixtureLinear(ctx, SSAM_F_RHO, p->rho1, p->rho2);
+}
+
+ssam_status ssam_mixture_cp(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    return mixtureLinear(ctx, SSAM_F_CP, p->cp1, p->cp2);
+}
+
+ssam_status ssam_mixture_k(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(need(ctx, SSAM_F_T, "temp"));
+    double s1, s2;
+    TRY(unitsShift(ctx, p->k1, &s1));
+    TRY(unitsShift(ctx, p->k2, &s2));
+    TRY(ensureField(ctx, SSAM_F_K));
+    KStage s{*p, s1, s2, ctx->plane[SSAM_F_ALPHA1][0], ctx->plane[SSAM_F_T][0], ctx->plane[SSAM_F_K][0]};
+    LAUNCH((k_map<KStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    ctx->isSet[SSAM_F_K] = true;
+    return finish(ctx);
+}
+
+ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(ensureField(ctx, SSAM_F_RHO_SOLVER));
+    TRY(ensureField(ctx, SSAM_F_RHOCP));
+    SolverRhoStage s{*p, ctx->plane[SSAM_F_ALPHA1][0], ctx->plane[SSAM_F_RHO_SOLVER][0], ctx->plane[SSAM_F_RHOCP][0]};
+    LAUNCH((k_map<SolverRhoStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    ctx->isSet[SSAM_F_RHO_SOLVER] = ctx->isSet[SSAM_F_RHOCP] = true;
+    return finish(ctx);
+}
+
+ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    CHECK(p->model == SSAM_STICK_CONSTANT || p->model == SSAM_STICK_EXPONENTIAL, SSAM_ERR_UNKNOWN_MODEL,
+          "Unknown stickModel type");
+    TRY(need(ctx, SSAM_F_MUEFF, "muEff"));
+    TRY(need(ctx, SSAM_F_EPSDOT, "epsilonDotEq"));
+    TRY(ensureField(ctx, SSAM_F_QVISC));
+    QviscStage s{p->betaTQ, ctx->plane[SSAM_F_MUEFF][0], ctx->plane[SSAM_F_EPSDOT][0], ctx->plane[SSAM_F_QVISC][0]};
+    LAUNCH((k_map<QviscStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    ctx->isSet[SSAM_F_QVISC] = true;
+    if (p->fricPatch >= 0) TRY(launchQfric(ctx, *p));
+    return finish(ctx);
+}
+
+ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* area) {
+    CHECK(ctx && centre && area, SSAM_ERR_INVALID, "null argument");
+    CHECK(ctx->fricPatchCached >= 0, SSAM_ERR_INVALID, "no friction patch evaluated yet");
+    double s[4];
+    CU(cudaMemcpyAsync(s, ctx->fricSums + 4, sizeof(s), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    centre[0] = s[0] / s[3];
+    centre[1] = s[1] / s[3];
+    centre[2] = s[2] / s[3];
+    *area = s[3];
+    return SSAM_OK;
+}
+
+// ---- fused update ---------------------------------------------------------------------------------------------
+static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, int flags) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(checkViscModel(ctx, &p->visc1));
+    TRY(checkViscModel(ctx, &p->visc2));
+    CHECK(p->visc2.model == SSAM_VISC_NEWTONIAN, SSAM_ERR_INVALID,
+          "fused path: phase 2 must be Newtonian (two viscoplastic phases clash on sigmaf/sigmay, SURVEY D-2); "
+          "use the staged calls");
+    TRY(need(ctx, SSAM_F_U, "U"));
+    TRY(need(ctx, SSAM_F_T, "temp"));
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    UpdateArgs a;
+    fillMeshArgs(ctx, a);
+    TRY(unitsShift(ctx, p->mix.k1, &a.kshift1));
+    TRY(unitsShift(ctx, p->mix.k2, &a.kshift2));
+    const int model1 = p->visc1.model;
+    const bool hasSigma = model1 == SSAM_VISC_SHEPPARD_WRIGHT || model1 == SSAM_VISC_FKS;
+    const int outs[] = {SSAM_F_EPSDOT, SSAM_F_NU1, SSAM_F_NU2, SSAM_F_NU,  SSAM_F_MUEFF,
+                        SSAM_F_RHO,    SSAM_F_CP,  SSAM_F_K,   SSAM_F_QVISC};
+    for (int f : outs) TRY(ensureField(ctx, f));
+    if (hasSigma) {
+        TRY(ensureField(ctx, SSAM_F_SIGMAF));
+        TRY(ensureField(ctx, SSAM_F_SIGMAY));
+    }
+    if (model1 == SSAM_VISC_NORTON_HOFF) TRY(ensureField(ctx, SSAM_F_STRAINRATE));
+    if (flags & 1) {
+        TRY(ensureField(ctx, SSAM_F_GRADU));
+        for (int k = 0; k < 9; ++k) a.gradU[k] = ctx->plane[SSAM_F_GRADU][k];
+        a.writeGrad = 1;
+    }
+    a.T = ctx->plane[SSAM_F_T][0];
+    a.alpha = ctx->plane[SSAM_F_ALPHA1][0];
+    a.eps = ctx->plane[SSAM_F_EPSDOT][0];
+    a.sr = ctx->plane[SSAM_F_STRAINRATE][0];
+    a.nu1 = ctx->plane[SSAM_F_NU1][0];
+    a.nu2 = ctx->plane[SSAM_F_NU2][0];
+    a.sigmaf = ctx->plane[SSAM_F_SIGMAF][0];
+    a.sigmay = ctx->plane[SSAM_F_SIGMAY][0];
+    a.nu = ctx->plane[SSAM_F_NU][0];
+    a.mu = ctx->plane[SSAM_F_MUEFF][0];
+    a.rho = ctx->plane[SSAM_F_RHO][0];
+    a.cp = ctx->plane[SSAM_F_CP][0];
+    a.k = ctx->plane[SSAM_F_K][0];
+    a.qvisc = ctx->plane[SSAM_F_QVISC][0];
+    a.prm = *p;
+
+    if (ctx->nProcPatches && (flags & 2)) {
+        TRY(haloExchangeField(ctx, SSAM_F_U));
+        TRY(haloExchangeField(ctx, SSAM_F_T));
+        TRY(haloExchangeField(ctx, SSAM_F_ALPHA1));
+    }
+    TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
+    if (ctx->nProcPatches) {
+        TRY(haloExchangeField(ctx, SSAM_F_EPSDOT));
+        if (model1 == SSAM_VISC_NORTON_HOFF) TRY(haloExchangeField(ctx, SSAM_F_STRAINRATE));
+        if (flags & 1) TRY(haloExchangeField(ctx, SSAM_F_GRADU));
+    }
+    TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, true)));
+    for (int f : outs) ctx->isSet[f] = true;
+    if (hasSigma) ctx->isSet[SSAM_F_SIGMAF] = ctx->isSet[SSAM_F_SIGMAY] = true;
+    if (model1 == SSAM_VISC_NORTON_HOFF) ctx->isSet[SSAM_F_STRAINRATE] = true;
+    if (flags & 1) ctx->isSet[SSAM_F_GRADU] = true;
+    if (p->stick.fricPatch >= 0) TRY(launchQfric(ctx, p->stick));
+    return SSAM_OK;
+}
+
+ssam_status ssam_update_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags) {
+    TRY(updateFusedAsync(ctx, p, flags));
+    return finish(ctx);
+}
+
+ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io) {
+    CHECK(ctx && p && io, SSAM_ERR_INVALID, "null argument");
+    CHECK(io->U_i && io->T_i && io->alpha1_i, SSAM_ERR_INVALID, "U, temp and alpha1 host buffers are required");
+    struct In {
+        int f;
+        const double *i, *b;
+    } ins[] = {{SSAM_F_U, io->U_i, io->U_b},
+               {SSAM_F_T, io->T_i, io->T_b},
+               {SSAM_F_ALPHA1, io->alpha1_i, io->alpha1_b},
+               {SSAM_F_P, io->p_i, io->p_b}};
+    TRY(ensureStage(ctx, size_t(ctx->nTot) * 3));
+    for (const In& in : ins) {
+        if (!in.i) continue;
+        TRY(ensureField(ctx, in.f));
+        const int nc = ncompOf(in.f);
+        if (nc == 1) {
+            TRY(uploadAoS(ctx, in.i, ctx->nCells, 1, ctx->plane[in.f], 0));
+            if (in.b) TRY(uploadAoS(ctx, in.b, ctx->nBnd, 1, ctx->plane[in.f], ctx->nCells));
+        } else {
+            // one staging buffer holds internal + boundary AoS, two transposes, no intermediate sync
+            CU(cudaMemcpyAsync(ctx->stage, in.i, size_t(ctx->nCells) * nc * sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->stream));
+            PlanePtrs pl;
+            for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? ctx->plane[in.f][k] : nullptr;
+            LAUNCH(k_aos_to_soa_n, gridFor((long long)ctx->nCells * nc, 256), 256, ctx->stage, ctx->nCells, nc, pl, 0);
+            if (in.b && ctx->nBnd) {
+                double* st2 = ctx->stage + size_t(ctx->nCells) * nc;
+                CU(cudaMemcpyAsync(st2, in.b, size_t(ctx->nBnd) * nc * sizeof(double), cudaMemcpyHostToDevice,
+                                   ctx->stream));
+                LAUNCH(k_aos_to_soa_n, gridFor((long long)ctx->nBnd * nc, 256), 256, st2, ctx->nBnd, nc, pl,
+                       ctx->nCells);
+            }
+        }
+        ctx->isSet[in.f] = true;
+    }
+    TRY(updateFusedAsync(ctx, p, ctx->nProcPatches ? 2 : 0));
+    for (int o = 0; o < io->nOut; ++o) {
+        const int f = io->outFields[o];
+        CHECK(f >= 0 && f < SSAM_F_COUNT && ncompOf(f) == 1, SSAM_ERR_INVALID, "host outputs must be scalar fields");
+        TRY(need(ctx, f, "requested output was not produced by this update"));
+        if (io->out_i && io->out_i[o])
+            CU(cudaMemcpyAsync(io->out_i[o], ctx->plane[f][0], size_t(ctx->nCells) * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->out_b && io->out_b[o] && ctx->nBnd)
+            CU(cudaMemcpyAsync(io->out_b[o], ctx->plane[f][0] + ctx->nCells, size_t(ctx->nBnd) * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+// ---- comm -----------------------------------------------------------------------------------------------------
+ssam_status ssam_comm_unique_id(void* id_out) {
+    ssam_ctx* ctx = nullptr;
+    CHECK(id_out, SSAM_ERR_INVALID, "null id buffer");
+    static_assert(sizeof(ncclUniqueId) <= SSAM_UNIQUE_ID_BYTES, "unique id size");
+    if (!nccl().load()) return fail(nullptr, SSAM_ERR_COMM, nccl().error);
+    ncclUniqueId id;
+    NC(nccl().GetUniqueId(&id));
+    std::memset(id_out, 0, SSAM_UNIQUE_ID_BYTES);
+    std::memcpy(id_out, &id, sizeof(id));
+    return SSAM_OK;
+}
+
+ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int nRanks) {
+    CHECK(ctx && id, SSAM_ERR_INVALID, "null argument");
+    CHECK(nRanks >= 1 && rank >= 0 && rank < nRanks, SSAM_ERR_INVALID, "bad rank / nRanks");
+    if (!nccl().load()) return fail(ctx, SSAM_ERR_COMM, nccl().error);
+    CU(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, sizeof(uid));
+    NC(nccl().CommInitRank(&ctx->comm, nRanks, uid, rank));
+    ctx->rank = rank;
+    ctx->nRanks = nRanks;
+    ctx->fricPatchCached = -1;
+    return SSAM_OK;
+}
+
+ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t mask) {
+    CHECK(ctx && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    for (int f = 0; f < SSAM_F_COUNT; ++f)
+        if (mask & (1u << f)) {
+            TRY(need(ctx, f, "halo exchange of a field that is not set"));
+            TRY(haloExchangeField(ctx, f));
+        }
+    return finish(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the oracle.
+
+Bars (BASELINE.json north_star): integer tables bit-exact; grad U / strain rates bit-exact (same
+summation order, no FMA); every other FP64 field <= 1e-11 relative per cell and boundary face.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from solidstateamfoam_b200 import capi, cases
+from solidstateamfoam_b200 import mesh as M
+from solidstateamfoam_b200 import params as P
+
+from helpers import EPS_FACTOR, SR_FACTOR, check_field, compare_ctx_oracle, oracle_case, oracle_update
+
+pytestmark = pytest.mark.gpu
+
+SHEAR = (1.0, 0.3, 0.1, 0.0, 1.0, 0.2, 0.0, 0.0, 1.0)
+
+
+def small_cases():
+    return {
+        "cfg1_hex": lambda: cases.cfg1(dims=(20, 16, 12)),
+        "cfg1_sheared_graded": lambda: cases.cfg1(dims=(16, 12, 10), affine=SHEAR, grading=(2.0, 0.5, 3.0)),
+        "cfg2_fks_kelvin": lambda: cases.cfg2(dims=(16, 16, 8)),
+        "cfg2_fks_celsius": lambda: cases.cfg2(dims=(12, 10, 8), units="Celsius"),
+        "cfg3_poly": lambda: cases.cfg3(base=(12, 12, 12)),
+        "cfg4_nortonhoff": lambda: cases.cfg4(dims=(12, 12, 12)),
+    }
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", list(small_cases()))
+def test_integer_addressing_bit_exact(ctx, name):
+    case = small_cases()[name]()
+    ctx.load_case(case)
+    oc = oracle_case(case)
+    for which in (P.ADDR_OWNER_START, P.ADDR_EXTRA_START, P.ADDR_EXTRA_FACE, P.ADDR_EXTRA_OTHER,
+                  P.ADDR_CELL_FACES_START, P.ADDR_CELL_FACES, P.ADDR_HALO_SEND_CELLS, P.ADDR_HALO_PATCH_OFFSETS,
+                  P.ADDR_FACE_COLOUR):
+        got, ref = ctx.addressing(which), oc.addressing(which)
+        assert got.dtype == ref.dtype and got.shape == ref.shape, P.ADDR_NAMES[which]
+        assert got.tobytes() == ref.tobytes(), f"{P.ADDR_NAMES[which]} differs"
+
+
+@pytest.mark.parametrize("name", list(small_cases()))
+def test_fused_update_matches_oracle(ctx, name):
+    case = small_cases()[name]()
+    ctx.load_case(case)
+    ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+    oc = oracle_update(case, O.FAITHFUL)
+    report = {}
+    compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU, P.F_U], report)
+    print(name, {k: (f"{v[0]:.1e}", v[1]) for k, v in report.items()})
+
+
+@pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly", "cfg4_nortonhoff"])
+def test_staged_calls_match_oracle_and_fused(ctx, name):
+    """The solver's own call sequence: thermo.correct() with the *stored* epsilonDotEq,
+    then TEqn.H's strain rate / mu / friction.correct() / cp / k."""
+    case = small_cases()[name]()
+    ctx.load_case(case)
+    oc = oracle_case(case)
+    p = case.params
+    nh = p.visc1.model == P.VISC_NORTON_HOFF
+    # previous time step's epsilonDotEq (createFluidFields.H:148-164 initial value): uniform 1.0
+    nTot = case.mesh.nCells + case.mesh.nBoundaryFaces
+    stale = np.full(nTot, 1.0)
+    ctx.upload(P.F_EPSDOT, stale[: case.mesh.nCells], stale[case.mesh.nCells:])
+    oc.set(P.F_EPSDOT, stale[: case.mesh.nCells], stale[case.mesh.nCells:])
+    # solveFluid.H:52  thermo.correct()
+    ctx.thermo_correct(p.visc1, p.visc2, p.mix)
+    oc.viscosity_correct(1, p.visc1)
+    oc.viscosity_correct(2, p.visc2)
+    oc.mixture("calc_nu", p.mix)
+    compare_ctx_oracle(ctx, oc, [P.F_NU1, P.F_NU2, P.F_NU] + ([] if nh else [P.F_SIGMAF, P.F_SIGMAY]))
+    # TEqn.H:3-15
+    ctx.strain_rate(EPS_FACTOR, P.F_EPSDOT)
+    ctx.mixture("mu", p.mix)
+    oc.strain_rate(EPS_FACTOR, P.F_EPSDOT)
+    oc.mixture("mu", p.mix)
+    if p.stick.fricPatch >= 0 or True:
+        ctx.friction_correct(p.stick)
+        oc.friction_correct(p.stick)
+    ctx.mixture("cp", p.mix)
+    ctx.mixture("k", p.mix)
+    ctx.mixture("rho", p.mix)
+    ctx.solver_rho_rhocp(p.mix)
+    ctx.grad_u()
+    for w in ("cp", "k", "rho"):
+        oc.mixture(w, p.mix)
+    oc.solver_rho_rhocp(p.mix)
+    fields = [P.F_EPSDOT, P.F_MUEFF, P.F_QVISC, P.F_CP, P.F_K, P.F_RHO, P.F_RHO_SOLVER, P.F_RHOCP, P.F_GRADU]
+    if p.stick.fricPatch >= 0:
+        fields.append(P.F_QFRIC)
+    compare_ctx_oracle(ctx, oc, fields)
+    # now the staged sequence in fused order must equal the fused kernel bit for bit
+    ctx.thermo_correct(p.visc1, p.visc2, p.mix)
+    ctx.mixture("mu", p.mix)
+    ctx.friction_correct(p.stick)
+    staged = {f: ctx.download(f) for f in case.outputs}
+    ctx.update_fused(p, 0)
+    for f in case.outputs:
+        gi, gb = ctx.download(f)
+        assert np.array_equal(gi, staged[f][0], equal_nan=True), P.FIELD_NAMES[f]
+        assert np.array_equal(gb, staged[f][1], equal_nan=True), P.FIELD_NAMES[f] + " (boundary)"
+
+
+def test_rotational_slip_bcs(ctx):
+    for case in (cases.cfg1(dims=(10, 9, 8)), cases.cfg3(base=(8, 8, 8))):
+        ctx.load_case(case)
+        oc = oracle_case(case)
+        gi, gb = ctx.download(P.F_U)
+        ref = oc.field(P.F_U)
+        # exp() in the exponential variant is the only non-IEEE op
+        bit = case.rotslip.model == P.ROTSLIP_CONSTANT
+        check_field("U_b", gb, ref[case.mesh.nCells:], bit)
+        assert np.array_equal(gi, ref[: case.mesh.nCells])
+
+
+def test_friction_patch_centre(ctx):
+    case = cases.cfg1(dims=(12, 10, 8), affine=SHEAR)
+    ctx.load_case(case)
+    ctx.update_fused(case.params, 0)
+    oc = oracle_update(case)
+    c_gpu, a_gpu = ctx.friction_patch_centre()
+    c_ref, a_ref = oc.friction_patch_centre()
+    assert np.array_equal(c_gpu, c_ref) and a_gpu == a_ref  # serial in-order sum: bit-exact
+
+
+def test_ten_updates_cfg1(ctx):
+    """cfg1: 10 updates with U, T advanced analytically per step, compared every step."""
+    case = cases.cfg1(dims=(16, 16, 8))
+    ctx.mesh_set(case.mesh, case.patch_u_bc)
+    for step in range(10):
+        cases.advance(case, step)
+        ctx.upload(P.F_U, case.U_i, case.U_b)
+        ctx.upload(P.F_T, case.T_i, case.T_b)
+        ctx.upload(P.F_ALPHA1, case.alpha1_i, case.alpha1_b)
+        ctx.upload(P.F_P, case.p_i, case.p_b)
+        ctx.bc_rotational_slip(case.rotslip)
+        ctx.update_fused(case.params, 0)
+        oc = oracle_update(case)
+        compare_ctx_oracle(ctx, oc, case.outputs)
+
+
+def test_error_behaviour(ctx):
+    case = cases.cfg4(dims=(6, 6, 6))
+    ctx.load_case(case)
+    # NortonHoff registers no sigmay: calcQfric's lookup aborts in the reference (SURVEY D-1)
+    ctx.update_fused(case.params, 0)
+    stick = P.constant_slip_stick(case.mesh.patch_id("zmax"), 0.9, 0.5, cases.OMEGA, 0.3)
+    with pytest.raises(capi.SsamError) as e:
+        ctx.friction_correct(stick)
+    assert e.value.status == P.ERR_MISSING_FIELD
+    bad = P.ViscosityParams(model=17)
+    with pytest.raises(capi.SsamError) as e:
+        ctx.viscosity_correct(1, bad)
+    assert e.value.status == P.ERR_UNKNOWN_MODEL
+    mix = P.mixture(1.0, 1.0, 1.0, 1.0, P.k_cubic(1, 1, 1, 1, 0, 1, units="Rankine"), P.k_constant(1.0))
+    with pytest.raises(capi.SsamError) as e:
+        ctx.mixture("k", mix)
+    assert e.value.status == P.ERR_UNITS
+    badstick = P.StickParams(model=7, fricPatch=0, betaTQ=1.0)
+    with pytest.raises(capi.SsamError) as e:
+        ctx.friction_correct(badstick)
+    assert e.value.status == P.ERR_UNKNOWN_MODEL
+
+
+def test_edge_values(ctx):
+    """eDot = 0 and below eDotMin, T below Ta / above Tm, alpha outside [0,1], Celsius clamp at 0 (NaN)."""
+    case = cases.cfg2(dims=(8, 8, 8), units="Celsius")
+    n = case.mesh.nCells
+    case.T_i[:8] = [0.0, 100.0, 292.9, 293.0, 855.0, 3000.0, 273.0, 1e-3]
+    case.alpha1_i[:6] = [-0.5, 0.0, 1e-300, 1.0, 1.5, 0.5]
+    case.U_i[:] = 0.0          # eDot exactly 0 in the interior
+    case.U_b[:] = 0.0
+    case.rotslip = None
+    # Celsius fit with Tmin = 0: T = 273 K clamps to exactly 0 -> k0*(0/0) = NaN (SURVEY D-4)
+    case.params.mix.k1.Tmin = 0.0
+    ctx.load_case(case)
+    ctx.update_fused(case.params, 0)
+    oc = oracle_update(case)
+    compare_ctx_oracle(ctx, oc, case.outputs)
+    ki, _ = ctx.download(P.F_K)
+    assert np.isnan(ki[6]) and np.isnan(oc.field(P.F_K)[6])
