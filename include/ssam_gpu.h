@@ -178,6 +178,12 @@ SSAM_API ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking);
 SSAM_API int ssam_abi_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 SSAM_API int64_t ssam_launch_count(const ssam_ctx* ctx);
+/* Per-kernel timing for the roofline figure: when enabled, every fused update brackets its cell
+ * kernel (the dominant kernel) with CUDA events on the launching stream.  ssam_profile_get
+ * synchronises, returns the summed cell-kernel milliseconds and the number of launches since the
+ * last call, and resets both. */
+SSAM_API ssam_status ssam_profile_enable(ssam_ctx* ctx, int enable);
+SSAM_API ssam_status ssam_profile_get(ssam_ctx* ctx, double* cells_ms_total, int64_t* n_launches);
 
 /* ---- mesh + integer addressing ------------------------------------------------------------------ */
 SSAM_API ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* mesh);

@@ -56,6 +56,10 @@ struct ssam_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, nRanks = 1;
 
+    // optional per-kernel timing (ssam_profile_enable)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
+
     // lazily built integer tables
     int *cellFacesStart = nullptr, *cellFaces = nullptr, *faceColour = nullptr;
 };
@@ -545,6 +549,29 @@ ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking) {
 
 int64_t ssam_launch_count(const ssam_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+ssam_status ssam_profile_enable(ssam_ctx* ctx, int enable) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    ctx->profile = enable != 0;
+    return SSAM_OK;
+}
+
+ssam_status ssam_profile_get(ssam_ctx* ctx, double* ms, int64_t* n) {
+    CHECK(ctx && ms && n, SSAM_ERR_INVALID, "null argument");
+    CU(cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    for (auto& pr : ctx->profEvents) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, pr.first, pr.second));
+        total += double(t);
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *ms = total;
+    *n = int64_t(ctx->profEvents.size());
+    ctx->profEvents.clear();
+    return SSAM_OK;
+}
+
 // ---- mesh -------------------------------------------------------------------------------------------
 ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     CHECK(ctx && m, SSAM_ERR_INVALID, "null argument");
@@ -965,7 +992,17 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         TRY(haloExchangeField(ctx, SSAM_F_T));
         TRY(haloExchangeField(ctx, SSAM_F_ALPHA1));
     }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->profile) {
+        CU(cudaEventCreate(&ev0));
+        CU(cudaEventCreate(&ev1));
+        CU(cudaEventRecord(ev0, ctx->stream));
+    }
     TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
+    if (ctx->profile) {
+        CU(cudaEventRecord(ev1, ctx->stream));
+        ctx->profEvents.emplace_back(ev0, ev1);
+    }
     if (ctx->nProcPatches) {
         TRY(haloExchangeField(ctx, SSAM_F_EPSDOT));
         if (model1 == SSAM_VISC_NORTON_HOFF) TRY(haloExchangeField(ctx, SSAM_F_STRAINRATE));

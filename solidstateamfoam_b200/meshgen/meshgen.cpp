@@ -191,21 +191,22 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                 }
             }
 
-    // patch order: physical sides in side order, then processor sides by neighbour rank
-    std::vector<int> order;
-    for (int s = 0; s < 6; ++s)
-        if (sideNbrRank[s] < 0) order.push_back(s);
+    // patch order: the six physical patches in side order on every rank -- decomposePar keeps every
+    // physical patch on every processor mesh, with zero faces where the side is a processor boundary,
+    // so patch indices (fricPatch!) are the same on all ranks -- then processor sides by neighbour rank
+    std::vector<std::pair<int, bool>> order;  // (side, asProcessorPatch)
+    for (int s = 0; s < 6; ++s) order.push_back({s, false});
     std::vector<int> procSides;
     for (int s = 0; s < 6; ++s)
         if (sideNbrRank[s] >= 0) procSides.push_back(s);
     std::stable_sort(procSides.begin(), procSides.end(),
                      [&](int a, int b) { return sideNbrRank[a] < sideNbrRank[b]; });
-    for (int s : procSides) order.push_back(s);
+    for (int s : procSides) order.push_back({s, true});
 
-    std::vector<int64_t> procFaceBegin;
-    for (int s : order) {
+    for (auto& so : order) {
+        const int s = so.first;
+        const bool isProc = so.second;
         m.patchStart.push_back(int32_t(f));
-        const bool isProc = sideNbrRank[s] >= 0;
         m.patchKind.push_back(isProc ? PROCESSOR : GENERIC);
         m.patchNbrRank.push_back(isProc ? sideNbrRank[s] : -1);
         m.patchName.push_back(isProc ? ("procBoundary" + std::to_string(myRank) + "to" +
@@ -215,6 +216,10 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
         const bool hi = (s % 2) == 1;
         const double sgn = hi ? 1.0 : -1.0;
         const int64_t f0 = f;
+        if (!isProc && sideNbrRank[s] >= 0) {
+            m.patchSize.push_back(0);  // physical patch with no faces on this rank
+            continue;
+        }
         if (axis == 0) {
             const int i = hi ? nx - 1 : 0;
             for (int k = 0; k < nz; ++k)

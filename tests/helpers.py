@@ -26,8 +26,16 @@ def oracle_case(case, apply_bc=True):
     return oc
 
 
-def oracle_update(case, form=O.FAITHFUL):
+def oracle_update(case, form=O.FAITHFUL, ctx=None):
+    """Full update on the oracle.  With `ctx`, U is taken from the GPU context: the exponential
+    rotational-slip BC contains an exp(), so its U_b agrees with the oracle's to ~1 ulp rather than
+    bit for bit, and the bit-exact gradient comparison needs identical inputs on both sides (the BC
+    itself is compared separately, test_rotational_slip_bcs)."""
     oc = oracle_case(case)
+    if ctx is not None:
+        gi, gb = ctx.download(P.F_U)
+        check_field("U (BC output)", np.concatenate([gi, gb]), oc.field(P.F_U), False)
+        oc.set(P.F_U, gi, gb)
     oc.update(case.params, form=form)
     return oc
 

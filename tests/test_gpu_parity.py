@@ -56,7 +56,7 @@ def test_fused_update_matches_oracle(ctx, name):
     case = small_cases()[name]()
     ctx.load_case(case)
     ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
-    oc = oracle_update(case, O.FAITHFUL)
+    oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
     report = {}
     compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU, P.F_U], report)
     print(name, {k: (f"{v[0]:.1e}", v[1]) for k, v in report.items()})
@@ -69,6 +69,7 @@ def test_staged_calls_match_oracle_and_fused(ctx, name):
     case = small_cases()[name]()
     ctx.load_case(case)
     oc = oracle_case(case)
+    oc.set(P.F_U, *ctx.download(P.F_U))  # identical inputs on both sides (see helpers.oracle_update)
     p = case.params
     nh = p.visc1.model == P.VISC_NORTON_HOFF
     # previous time step's epsilonDotEq (createFluidFields.H:148-164 initial value): uniform 1.0
