@@ -270,6 +270,11 @@ typedef struct ssam_host_io {
 } ssam_host_io;
 SSAM_API ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io);
 
+/* ---- test hook ---------------------------------------------------------------------------------------
+ * Evaluates one of the device math routines of csrc/fastmath.cuh on host arrays (tests/test_gpu_math.py):
+ * fn 0 log, 1 exp, 2 pow(x,y), 3 asinh, 4 exact division x/y, 5 operator / , 6 x/x, 7 asinh(exp(x)). */
+SSAM_API ssam_status ssam_debug_math(ssam_ctx* ctx, int fn, const double* x, const double* y, double* out, int64_t n);
+
 /* ---- multi-GPU: processor-patch halos over NCCL --------------------------------------------------
  * Replaces processorFvPatchField initEvaluate/evaluate (OpenFOAM, triggered by
  * correctBoundaryConditions()) and the reduce() pair in constantSlipStick.C:134-135. */

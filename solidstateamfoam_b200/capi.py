@@ -23,7 +23,7 @@ SYMBOLS = [
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
     "ssam_solver_rho_rhocp", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
-    "ssam_update_fused_host", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
+    "ssam_update_fused_host", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
 ]
 
 
@@ -82,6 +82,7 @@ def load():
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
     L.ssam_update_fused_host.argtypes = [vp, C.POINTER(P.UpdateParams), C.POINTER(P.HostIO)]
+    L.ssam_debug_math.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int64]
     L.ssam_comm_unique_id.argtypes = [vp]
     L.ssam_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ssam_halo_exchange.argtypes = [vp, C.c_uint32]
@@ -243,6 +244,13 @@ class Context:
 
     def update_fused_host(self, p: P.UpdateParams, io: P.HostIO):
         self._chk(self.L.ssam_update_fused_host(self.h, C.byref(p), C.byref(io)))
+
+    def debug_math(self, fn: int, x, y=None) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        yy = None if y is None else np.ascontiguousarray(np.broadcast_to(y, x.shape), dtype=np.float64)
+        out = np.empty_like(x)
+        self._chk(self.L.ssam_debug_math(self.h, fn, _dptr(x), _dptr(yy), _dptr(out), x.size))
+        return out
 
     # comm -----------------------------------------------------------------------------------------
     @staticmethod

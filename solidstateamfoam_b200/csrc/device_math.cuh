@@ -9,11 +9,10 @@
 #pragma once
 #include <cstdint>
 
+#include "fastmath.cuh"
 #include "ssam_gpu.h"
 
 namespace ssam {
-
-#define SSAM_DEV __device__ __forceinline__
 
 constexpr double kSMALL = 1e-15;    // Foam::SMALL
 constexpr double kVSMALL = 1e-300;  // Foam::VSMALL
@@ -46,37 +45,67 @@ struct ViscOut {
     double nu, sigmaf, sigmay;
 };
 
-// SheppardWright.C:51-118; correct() SheppardWright.H:133-138
-SSAM_DEV ViscOut sheppardWright(const ssam_viscosity_params& p, double T, double e) {
+// Parameter-only sub-expressions.  The reference evaluates these dimensionedScalar expressions on the
+// host (libm) once per call; so do we (deriveVisc() in ssam_abi.cu), instead of once per cell.
+struct ViscDerived {
+    double invN;        // 1/n_                                   SheppardWright.C:74
+    double threeRho;    // 3.0*rho_                               SheppardWright.C:115, FKS.C:178
+    double logA;        // log(A_)          (log-domain form of pow(Z/A, 1/n))
+    double log01;       // log(0.1)         (e01 in sigmay(), SheppardWright.C:85)
+    double Hcoef;       // a1_ + (a2_*1.571)                      FKS.C:73
+    double TmTa;        // Tm_ - Ta_                              FKS.C:112
+    double negC1;       // -c1_                                   FKS.C:99
+    double invC2;       // 1/c2_                                  FKS.C:99
+    double b3LogY;      // b3_*log(e01_/e0_ + VSMALL)             FKS.C:152
+    double mu0OverRho;  // mu0_/rho_                              NortonHoff.C:60
+    double mMinus1;     // m_ - 1                                 NortonHoff.C:63
+    double sqrt3;       // sqrt(3.0)                              NortonHoff.C:62
+    int b2IsOne;        // pow(x, 1.0) == x exactly
+    int invC2IsOne;
+};
+
+// SheppardWright.C:51-118; correct() SheppardWright.H:133-138.
+// pow(Z/A, 1/n) with Z = eDot*exp(Q/(R T)) is evaluated in the log domain,
+//   log(Z/A) = log(eDot) + Q/(R T) - log(A),
+// which needs neither exp(Q/RT) nor a pow(): abs. error of the exponent ~6e-15 -> relative ~2e-15
+// after the 1/n, the same size as the reference's own rounding of exp(58).
+SSAM_DEV double swAsinhOfLog(double t) {
+    // asinh(exp(t)): for exp(t) >= 2^28, asinh(P) = log(2P) = t + ln2 to double precision
+    if (t > 19.5) return t + kLn2;
+    return fastAsinh(fastExp(t));
+}
+SSAM_DEV ViscOut sheppardWright(const ssam_viscosity_params& p, const ViscDerived& d, double T, double e) {
     ViscOut o;
-    const double ex = exp(p.Q / (p.R * T));  // shared by Z() (:64) and sigmay() (:91): same bits
-    const double Z = e * ex;
-    const double rn = 1 / p.n;
-    o.sigmaf = p.sigmaR * asinh(pow(Z / p.A, rn));           // :74
-    o.sigmay = p.sigmaR * asinh(pow((0.1 * ex) / p.A, rn));  // :91
-    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, o.sigmaf / ((3.0 * p.rho) * ofMax(e, p.eDotMin))));  // :109-117
+    const double q = divExact(p.Q, p.R * T);  // Q_/(R_*temp_)  :64
+    const double qa = q - d.logA;
+    o.sigmaf = p.sigmaR * swAsinhOfLog((fastLog(e) + qa) * d.invN);   // :74
+    o.sigmay = p.sigmaR * swAsinhOfLog((d.log01 + qa) * d.invN);      // :91
+    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divExact(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :109-117
     return o;
 }
 
 // FKS.C:63-183; correct() FKS.H:156-161
-SSAM_DEV ViscOut fks(const ssam_viscosity_params& p, double T, double e) {
+SSAM_DEV ViscOut fks(const ssam_viscosity_params& p, const ViscDerived& d, double T, double e) {
     ViscOut o;
-    const double Tlim = ofMin(ofMax(T, p.Ta), p.Tm);                       // :108
-    const double Th = (Tlim - p.Ta) / (p.Tm - p.Ta);                       // :112
-    const double H = ((p.a1 + (p.a2 * 1.571)) * T) / T;                    // :73
-    const double pw = p.b1 * pow(Th + kSMALL, p.b2);                       // :89 / :152
-    const double Lam = 1.0 + pw * (p.b3 * log(e / p.e0 + kVSMALL));        // :89
-    const double Theta = 1.0 - 1.0 / pow(1.0 + exp((-p.c1) * Th), 1 / p.c2);  // :99
-    o.sigmaf = (H * Lam) * Theta;                                           // :129
-    o.sigmay = (p.a1 * Theta) * (1.0 + pw * (p.b3 * log(0.1 / p.e0 + kVSMALL)));  // :152
-    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, o.sigmaf / ((3.0 * p.rho) * ofMax(e, p.eDotMin))));  // :172-181
+    const double Tlim = ofMin(ofMax(T, p.Ta), p.Tm);                      // :108
+    const double Th = divExact(Tlim - p.Ta, d.TmTa);                      // :112
+    const double H = divExact(d.Hcoef * T, T);                            // :73  (X*T)/T, NaN at T = 0
+    const double base = Th + kSMALL;
+    const double pw = p.b1 * (d.b2IsOne ? base : fastPow(base, p.b2));    // :89 / :152
+    const double Lam = 1.0 + pw * (p.b3 * fastLog(divExact(e, p.e0) + kVSMALL));  // :89
+    const double z = 1.0 + fastExp(d.negC1 * Th);
+    const double Theta = 1.0 - divExact(1.0, d.invC2IsOne ? z : fastPow(z, d.invC2));  // :99
+    o.sigmaf = (H * Lam) * Theta;                                         // :129
+    o.sigmay = (p.a1 * Theta) * (1.0 + pw * d.b3LogY);                    // :152
+    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divExact(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :172-181
     return o;
 }
 
-// NortonHoff.C:53-66, sr = viscosityModel::strainRate() = sqrt(2)*mag(symm(grad U))
-SSAM_DEV double nortonHoff(const ssam_viscosity_params& p, double sr) {
+// NortonHoff.C:53-66, sr = viscosityModel::strainRate() = sqrt(2)*mag(symm(grad U)); the division by
+// strainRateUnits_ = 1 is the identity
+SSAM_DEV double nortonHoff(const ssam_viscosity_params& p, const ViscDerived& d, double sr) {
     return ofMax(p.nuMin,
-                 ofMin(p.nuMax, (p.mu0 / p.rho) * pow((sqrt(3.0) * ofMax(sr, p.strainRateEffMin)) / 1.0, p.m - 1)));
+                 ofMin(p.nuMax, d.mu0OverRho * fastPow(d.sqrt3 * ofMax(sr, p.strainRateEffMin), d.mMinus1)));
 }
 
 // ---- mixture (incompressibleTwoPhaseThermalMixture.C) ----------------------------------------------
@@ -106,11 +135,11 @@ SSAM_DEV double qfricOf(const ssam_stick_params& p, double magOmega, double alph
                         double magR) {
     double inner;
     if (p.model == SSAM_STICK_CONSTANT) {
-        inner = (((1.0 - p.delta) * p.betaTQ) * sigmay) / sqrt(3.0) + (p.delta * p.muf) * pr;
+        inner = divExact(((1.0 - p.delta) * p.betaTQ) * sigmay, sqrt(3.0)) + (p.delta * p.muf) * pr;
     } else {
-        const double d = 1.0 - exp(((-magOmega) * magR) / ((p.delta0 * p.omega0) * p.Rs));
-        const double mf = p.mu0 * exp((((-p.lambda) * d) * magOmega) * magR);
-        inner = (((1.0 - d) * p.betaTQ) * sigmay) / sqrt(3.0) + (d * mf) * pr;
+        const double d = 1.0 - fastExp(divExact((-magOmega) * magR, (p.delta0 * p.omega0) * p.Rs));
+        const double mf = p.mu0 * fastExp((((-p.lambda) * d) * magOmega) * magR);
+        inner = divExact(((1.0 - d) * p.betaTQ) * sigmay, sqrt(3.0)) + (d * mf) * pr;
     }
     return ((1.0 * alpha) * inner) * (magOmega * magR);
 }

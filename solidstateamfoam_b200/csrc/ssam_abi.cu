@@ -287,6 +287,27 @@ ssam_status unitsShift(ssam_ctx* ctx, const ssam_conductivity& k, double* shift)
     return SSAM_OK;
 }
 
+// dimensionedScalar sub-expressions the reference evaluates on the host, with the host's libm
+ViscDerived deriveVisc(const ssam_viscosity_params& p) {
+    ViscDerived d;
+    std::memset(&d, 0, sizeof(d));
+    d.invN = 1 / p.n;
+    d.threeRho = 3.0 * p.rho;
+    d.logA = std::log(p.A);
+    d.log01 = std::log(0.1);
+    d.Hcoef = p.a1 + (p.a2 * 1.571);
+    d.TmTa = p.Tm - p.Ta;
+    d.negC1 = -p.c1;
+    d.invC2 = 1 / p.c2;
+    d.b3LogY = p.b3 * std::log(0.1 / p.e0 + 1e-300);
+    d.mu0OverRho = p.mu0 / p.rho;
+    d.mMinus1 = p.m - 1;
+    d.sqrt3 = std::sqrt(3.0);
+    d.b2IsOne = (p.b2 == 1.0) ? 1 : 0;
+    d.invC2IsOne = (d.invC2 == 1.0) ? 1 : 0;
+    return d;
+}
+
 ssam_status checkViscModel(ssam_ctx* ctx, const ssam_viscosity_params* p) {
     CHECK(p != nullptr, SSAM_ERR_INVALID, "null viscosity params");
     CHECK(p->model >= SSAM_VISC_NEWTONIAN && p->model <= SSAM_VISC_NORTON_HOFF, SSAM_ERR_UNKNOWN_MODEL,
@@ -447,6 +468,7 @@ ssam_status viscosityCorrect(ssam_ctx* ctx, int phase, const ssam_viscosity_para
     TRY(ensureField(ctx, nuField));
     ViscStage s;
     s.p = *p;
+    s.d = deriveVisc(*p);
     s.T = s.eps = s.sr = nullptr;
     s.sigmaf = s.sigmay = nullptr;
     s.nu = ctx->plane[nuField][0];
@@ -986,6 +1008,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     a.k = ctx->plane[SSAM_F_K][0];
     a.qvisc = ctx->plane[SSAM_F_QVISC][0];
     a.prm = *p;
+    a.d1 = deriveVisc(p->visc1);
 
     if (ctx->nProcPatches && (flags & 2)) {
         TRY(haloExchangeField(ctx, SSAM_F_U));
@@ -1070,6 +1093,27 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
                                cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+// ---- device-math evaluation (tests) -----------------------------------------------------------------------------
+ssam_status ssam_debug_math(ssam_ctx* ctx, int fn, const double* x, const double* y, double* out, int64_t n) {
+    CHECK(ctx && x && out && n >= 0, SSAM_ERR_INVALID, "null argument");
+    if (n == 0) return SSAM_OK;
+    double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+    TRY(devAlloc(ctx, &dx, size_t(n)));
+    TRY(devAlloc(ctx, &dout, size_t(n)));
+    CU(cudaMemcpyAsync(dx, x, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (y) {
+        TRY(devAlloc(ctx, &dy, size_t(n)));
+        CU(cudaMemcpyAsync(dy, y, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(k_debug_math, gridFor(n, 256), 256, fn, dx, dy, dout, (long long)n);
+    CU(cudaMemcpyAsync(out, dout, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dx);
+    cudaFree(dout);
+    if (dy) cudaFree(dy);
     return SSAM_OK;
 }
 
