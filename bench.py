@@ -232,6 +232,7 @@ def run_gpu(args):
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, n_ranks)
     ctx.load_case(case)
+    ctx.set_cell_kernel(args.cell_kernel)
     flags = capi.FUSED_HALO_INPUTS if n_ranks > 1 else 0
     ctx.set_blocking(False)
 
@@ -333,7 +334,7 @@ def run_gpu(args):
                        "parallelism": f"slab{n_ranks}" if n_ranks > 1 else "single",
                        "l2": "inputs larger than L2 (%.2f GB touched per update vs 126 MB L2)" %
                              (case.bytes_per_update / 1e9)},
-            "roofline": {"bound": "hbm", "kernel": "k_cells", "achieved": round(achieved, 1), "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_cells_tiled" if args.cell_kernel == 1 else "k_cells", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
                          "algorithmic_bytes_per_launch": bytes_cells, "kernel_ms": round(cells_avg_ms, 4),
                          "kernel_share_of_step": round(cells_avg_ms / (ms_total / args.steps), 4),
@@ -361,6 +362,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cell-kernel", type=int, default=1, choices=[0, 1],
+                    help="1 = tiled, bulk-async staged (default); 0 = one thread per cell, direct loads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

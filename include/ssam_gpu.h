@@ -178,6 +178,9 @@ SSAM_API ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking);
 SSAM_API int ssam_abi_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 SSAM_API int64_t ssam_launch_count(const ssam_ctx* ctx);
+/* Fused cell-kernel variant: 1 (default) = tiled, inputs of 256 consecutive cells staged in shared memory
+ * by 1-D bulk async copies; 0 = one thread per cell with direct global loads.  Results are identical. */
+SSAM_API ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant);
 /* Per-kernel timing for the roofline figure: when enabled, every fused update brackets its cell
  * kernel (the dominant kernel) with CUDA events on the launching stream.  ssam_profile_get
  * synchronises, returns the summed cell-kernel milliseconds and the number of launches since the

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -31,6 +32,9 @@ struct ssam_ctx {
     int *owner = nullptr, *neighbour = nullptr, *ownerStart = nullptr, *extraStart = nullptr;
     int2* extra = nullptr;
     int nExtra = 0;
+    int4* tileDesc = nullptr;
+    int nTiles = 0;
+    int cellKernel = 1;  // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged
     double *V = nullptr, *magSf_b = nullptr, *deltaCoeffs_b = nullptr;
     double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
     unsigned char* bndFlags = nullptr;
@@ -158,6 +162,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->ownerStart);
     devFree(c->extraStart);
     devFree(c->extra);
+    devFree(c->tileDesc);
     devFree(c->V);
     devFree(c->magSf_b);
     devFree(c->deltaCoeffs_b);
@@ -213,8 +218,8 @@ void rebuildBndFlags(ssam_ctx* c) {
 
 ssam_status buildAddressing(ssam_ctx* ctx) {
     const int nc = ctx->nCells, nIF = ctx->nIF, nF = ctx->nFaces;
-    TRY(devAlloc(ctx, &ctx->ownerStart, size_t(nc) + 1));
-    TRY(devAlloc(ctx, &ctx->extraStart, size_t(nc) + 1));
+    TRY(devAlloc(ctx, &ctx->ownerStart, size_t(nc) + 8));
+    TRY(devAlloc(ctx, &ctx->extraStart, size_t(nc) + 8));
     int* errFlag = nullptr;
     TRY(devAlloc(ctx, &errFlag, 1));
     CU(cudaMemsetAsync(errFlag, 0, sizeof(int), ctx->stream));
@@ -229,12 +234,16 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
     LAUNCH(k_extra_count, gridFor(nF, 256), 256, ctx->owner, ctx->neighbour, nIF, nF, ctx->extraStart);
     TRY(exclusiveScan(ctx, ctx->extraStart, nc + 1));
     ctx->nExtra = nIF + ctx->nBnd;
-    TRY(devAlloc(ctx, &ctx->extra, size_t(ctx->nExtra)));
+    TRY(devAlloc(ctx, &ctx->extra, size_t(ctx->nExtra) + 4));
     int* cursor = nullptr;
     TRY(devAlloc(ctx, &cursor, size_t(nc) + 1));
     CU(cudaMemcpyAsync(cursor, ctx->extraStart, (size_t(nc) + 1) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_extra_fill, gridFor(nF, 256), 256, ctx->owner, ctx->neighbour, ctx->bndFlags, nIF, nF, cursor, ctx->extra);
     LAUNCH(k_extra_sort, gridFor(nc, 256), 256, ctx->extraStart, nc, ctx->extra);
+    ctx->nTiles = gridFor(nc, TILE);
+    TRY(devAlloc(ctx, &ctx->tileDesc, size_t(ctx->nTiles)));
+    LAUNCH(k_tile_desc, gridFor(ctx->nTiles, 256), 256, ctx->ownerStart, ctx->extraStart, nc, ctx->nTiles,
+           ctx->tileDesc);
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(cursor);
     return SSAM_OK;
@@ -326,6 +335,7 @@ void fillMeshArgs(ssam_ctx* c, UpdateArgs& a) {
     a.ownerStart = c->ownerStart;
     a.extraStart = c->extraStart;
     a.extra = c->extra;
+    a.tileDesc = c->tileDesc;
     a.V = c->V;
     a.magSf_b = c->magSf_b;
     a.deltaCoeffs_b = c->deltaCoeffs_b;
@@ -435,6 +445,29 @@ ssam_status launchCellsBoundary(ssam_ctx* ctx, const UpdateArgs& a, int model1, 
     }
 #undef SSAM_DISPATCH
     return SSAM_OK;
+}
+
+template <int M>
+ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a) {
+    static bool configured = false;
+    const int smem = int(sizeof(TileSmem));
+    if (!configured) {
+        CU(cudaFuncSetAttribute(k_cells_tiled<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    k_cells_tiled<M><<<ctx->nTiles, TILE, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SSAM_OK;
+}
+ssam_status launchCellsTiled(ssam_ctx* ctx, const UpdateArgs& a, int model1) {
+    switch (model1) {
+        case SSAM_VISC_NEWTONIAN: return launchTiledOne<SSAM_VISC_NEWTONIAN>(ctx, a);
+        case SSAM_VISC_SHEPPARD_WRIGHT: return launchTiledOne<SSAM_VISC_SHEPPARD_WRIGHT>(ctx, a);
+        case SSAM_VISC_FKS: return launchTiledOne<SSAM_VISC_FKS>(ctx, a);
+        case SSAM_VISC_NORTON_HOFF: return launchTiledOne<SSAM_VISC_NORTON_HOFF>(ctx, a);
+    }
+    return fail(ctx, SSAM_ERR_UNKNOWN_MODEL, "Unknown viscosityModel type");
 }
 
 // fvc::grad(U) pieces: MODE_GRAD writes GRADU, MODE_STRAIN writes factor*mag(symm(grad U)) into outField
@@ -571,6 +604,13 @@ ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking) {
 
 int64_t ssam_launch_count(const ssam_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CHECK(variant == 0 || variant == 1, SSAM_ERR_INVALID, "cell kernel variant must be 0 (direct) or 1 (tiled)");
+    ctx->cellKernel = variant;
+    return SSAM_OK;
+}
+
 ssam_status ssam_profile_enable(ssam_ctx* ctx, int enable) {
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     ctx->profile = enable != 0;
@@ -628,7 +668,7 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
 
     const size_t nF = size_t(ctx->nFaces), nC = size_t(ctx->nCells), nB = size_t(ctx->nBnd);
     TRY(devAlloc(ctx, &ctx->owner, nF));
-    TRY(devAlloc(ctx, &ctx->neighbour, size_t(ctx->nIF)));
+    TRY(devAlloc(ctx, &ctx->neighbour, size_t(ctx->nIF) + 8));  // padded: bulk copies round to 16 bytes
     CU(cudaMemcpyAsync(ctx->owner, m->owner, nF * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->nIF)
         CU(cudaMemcpyAsync(ctx->neighbour, m->neighbour, size_t(ctx->nIF) * sizeof(int), cudaMemcpyHostToDevice,
@@ -646,7 +686,7 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
         cudaFree(dSf);
         cudaFree(dW);
     }
-    TRY(devAlloc(ctx, &ctx->V, nC));
+    TRY(devAlloc(ctx, &ctx->V, nC + 4));
     CU(cudaMemcpyAsync(ctx->V, m->V, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     TRY(devAlloc(ctx, &ctx->magSf_b, nB));
     TRY(devAlloc(ctx, &ctx->deltaCoeffs_b, nB));
@@ -1009,6 +1049,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     a.qvisc = ctx->plane[SSAM_F_QVISC][0];
     a.prm = *p;
     a.d1 = deriveVisc(p->visc1);
+    if (const char* dbg = std::getenv("SSAM_DBG")) a.dbg = std::atoi(dbg);
 
     if (ctx->nProcPatches && (flags & 2)) {
         TRY(haloExchangeField(ctx, SSAM_F_U));
@@ -1021,7 +1062,11 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, ctx->stream));
     }
-    TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
+    if (ctx->cellKernel == 1) {
+        TRY(launchCellsTiled(ctx, a, model1));
+    } else {
+        TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
+    }
     if (ctx->profile) {
         CU(cudaEventRecord(ev1, ctx->stream));
         ctx->profEvents.emplace_back(ev0, ev1);

@@ -51,15 +51,37 @@ def test_integer_addressing_bit_exact(ctx, name):
         assert got.tobytes() == ref.tobytes(), f"{P.ADDR_NAMES[which]} differs"
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["direct", "tiled"])
 @pytest.mark.parametrize("name", list(small_cases()))
-def test_fused_update_matches_oracle(ctx, name):
+def test_fused_update_matches_oracle(ctx, name, variant):
+    """both cell-kernel variants (one thread per cell with direct loads / tiled with bulk-async staging)"""
     case = small_cases()[name]()
     ctx.load_case(case)
-    ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+    ctx.set_cell_kernel(variant)
+    try:
+        ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+    finally:
+        ctx.set_cell_kernel(1)
     oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
     report = {}
     compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU, P.F_U], report)
     print(name, {k: (f"{v[0]:.1e}", v[1]) for k, v in report.items()})
+
+
+def test_tiled_kernel_capacity_fallback(ctx):
+    """a polyhedral tile whose owned faces exceed the staged capacity must fall back to global loads;
+    a mesh much larger than one tile exercises partial last tiles and cross-tile gathers"""
+    case = cases.cfg3(base=(20, 20, 20))
+    ctx.load_case(case)
+    res = {}
+    for variant in (0, 1):
+        ctx.set_cell_kernel(variant)
+        ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+        res[variant] = {f: ctx.download(f) for f in case.outputs + [P.F_GRADU]}
+    ctx.set_cell_kernel(1)
+    for f in res[0]:
+        assert np.array_equal(res[0][f][0], res[1][f][0], equal_nan=True), P.FIELD_NAMES[f]
+        assert np.array_equal(res[0][f][1], res[1][f][1], equal_nan=True), P.FIELD_NAMES[f]
 
 
 @pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly", "cfg4_nortonhoff"])
