@@ -233,3 +233,87 @@ def advance(case: Case, step: int) -> None:
     for pid in range(case.mesh.nPatches):
         if case.patch_u_bc[pid] == P.BC_ZERO_GRADIENT and case.mesh.patchKind[pid] == P.PATCH_GENERIC:
             case.U_b[case.mesh.patch_slice_b(pid)] = case.U_i[case.mesh.face_cells(pid)]
+
+
+# ---- OpenFOAM-style case directory for the C++ host mirror (host/case_driver.cpp) ------------------------
+def _visc_dict(v: P.ViscosityParams, rho, cp, kc: P.Conductivity) -> str:
+    def coeffs(name, keys, extra=()):
+        body = "\n".join(f"        {k} {getattr(v, k)!r};" for k in keys)
+        body += "".join(f"\n        {k} {val!r};" for k, val in extra)
+        return f"    transportModel {name};\n    {name}Coeffs\n    {{\n{body}\n    }}\n"
+
+    lim = [(k, getattr(v, k)) for k in ("nuMin", "nuMax", "eDotMin")]
+    if v.model == P.VISC_SHEPPARD_WRIGHT:
+        s = coeffs("SheppardWright", ["sigmaR", "Q", "R", "A", "n", "rho"], lim)
+    elif v.model == P.VISC_FKS:
+        s = coeffs("FKS", ["a1", "a2", "b1", "b2", "b3", "e0", "c1", "c2", "Tm", "Ta", "rho"], lim)
+    elif v.model == P.VISC_NORTON_HOFF:
+        s = coeffs("NortonHoff", ["mu0", "m", "rho", "nuMin", "nuMax", "strainRateEffMin"])
+    else:
+        s = f"    transportModel Newtonian;\n    nu {v.nu!r};\n"
+    s += f"    rho {rho!r};\n    cp {cp!r};\n"
+    if kc.kModel == P.K_CUBIC:
+        units = "Kelvin" if kc.units == P.UNITS_KELVIN else "Celsius"
+        s += (f"    kModel cubic;\n    k0 {kc.k0!r};\n    k1 {kc.k1!r};\n    k2 {kc.k2!r};\n    k3 {kc.k3!r};\n"
+              f"    Tmin {kc.Tmin!r};\n    Tmax {kc.Tmax!r};\n    units {units};\n")
+    else:
+        s += f"    kModel constant;\n    k {kc.k!r};\n"
+    return s
+
+
+def write_case_dir(path: str, case: Case, eps0: float = 1.0, mu0: float = 1.0) -> None:
+    """mesh.bin / fields.bin / patches.txt + constant/transportProperties, constant/frictionProperties, 0/U."""
+    import os
+
+    m = case.mesh
+    os.makedirs(os.path.join(path, "constant"), exist_ok=True)
+    os.makedirs(os.path.join(path, "0"), exist_ok=True)
+    nif = m.nInternalFaces
+    with open(os.path.join(path, "mesh.bin"), "wb") as fh:
+        np.array([m.nCells, nif, m.nFaces, m.nPatches], dtype=np.int32).tofile(fh)
+        for a in (m.owner, m.neighbour, m.patchStart, m.patchSize, m.patchKind, m.patchNbrRank, case.patch_u_bc):
+            np.ascontiguousarray(a, dtype=np.int32).tofile(fh)
+        for a in (m.Sf, m.weights, m.V, m.C, m.Cf[nif:], m.magSf[nif:], m.deltaCoeffs[nif:]):
+            np.ascontiguousarray(a, dtype=np.float64).tofile(fh)
+    with open(os.path.join(path, "patches.txt"), "w") as fh:
+        fh.write("\n".join(m.patchName) + "\n")
+    nb = m.nBoundaryFaces
+    with open(os.path.join(path, "fields.bin"), "wb") as fh:
+        for i, b in ((case.U_i, case.U_b), (case.T_i, case.T_b), (case.alpha1_i, case.alpha1_b), (case.p_i, case.p_b),
+                     (np.full(m.nCells, eps0), np.full(nb, eps0)), (np.full(m.nCells, mu0), np.full(nb, mu0))):
+            np.ascontiguousarray(i, dtype=np.float64).tofile(fh)
+            np.ascontiguousarray(b, dtype=np.float64).tofile(fh)
+    p = case.params
+    with open(os.path.join(path, "constant", "transportProperties"), "w") as fh:
+        fh.write("// written by solidstateamfoam_b200.cases.write_case_dir\nphases (metal air);\n\nmetal\n{\n")
+        fh.write(_visc_dict(p.visc1, p.mix.rho1, p.mix.cp1, p.mix.k1))
+        fh.write("}\n\nair\n{\n")
+        fh.write(_visc_dict(p.visc2, p.mix.rho2, p.mix.cp2, p.mix.k2))
+        fh.write("}\n\nsigma 0.07;\n")
+    s = p.stick
+    patch = m.patchName[s.fricPatch] if s.fricPatch >= 0 else "zmax"
+    om = "(" + " ".join(repr(x) for x in s.omega) + ")"
+    with open(os.path.join(path, "constant", "frictionProperties"), "w") as fh:
+        name = "constantSlipStick" if s.model == P.STICK_CONSTANT else "exponentialSlipStick"
+        fh.write(f"stickModel {name};\nalphaName alpha.metal;\npName p;\nfricPatch {patch};\n\n{name}Coeffs\n{{\n")
+        fh.write(f"    alphaName alpha.metal;\n    pName p;\n    fricPatch {patch};\n")
+        if s.model == P.STICK_CONSTANT:
+            fh.write(f"    betaTQ {s.betaTQ!r};\n    delta {s.delta!r};\n    omega {om};\n    muf {s.muf!r};\n")
+        else:
+            fh.write(f"    betaTQ {s.betaTQ!r};\n    omega {om};\n    omega0 {s.omega0!r};\n    delta0 {s.delta0!r};\n"
+                     f"    Rs {s.Rs!r};\n    mu0 {s.mu0!r};\n    lambda {s.lambda_!r};\n")
+        fh.write("}\n")
+    with open(os.path.join(path, "0", "U"), "w") as fh:
+        fh.write("dimensions [0 1 -1 0 0 0 0];\ninternalField uniform (0 0 0);\nboundaryField\n{\n")
+        r = case.rotslip
+        if r is not None:
+            omr = "(" + " ".join(repr(x) for x in r.omega) + ")"
+            vt = "(" + " ".join(repr(x) for x in r.Vt) + ")"
+            fh.write(f"    {m.patchName[r.patch]}\n    {{\n")
+            if r.model == P.ROTSLIP_CONSTANT:
+                fh.write(f"        type constantRotationalSlip;\n        omega {omr};\n        delta {r.delta!r};\n")
+            else:
+                fh.write(f"        type exponentialRotationalSlip;\n        omega {omr};\n        omega0 {r.omega0!r};\n"
+                         f"        delta0 {r.delta0!r};\n        R0 {r.R0!r};\n")
+            fh.write(f"        Vt {vt};\n        value uniform (0 0 0);\n    }}\n")
+        fh.write("}\n")

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""N-GPU parity check, one process per GPU (launch with torchrun / torch.distributed.run):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/multigpu_parity.py [--decomp slab|random]
+
+Every rank builds all partitions (small, deterministic), runs the multi-rank oracle (in-memory halo
+copies) on the CPU, and compares its own GPU partition -- NCCL halos of U, temp, alpha1, then of
+epsilonDotEq, and the 4-double all-reduce of the friction-patch sums -- against the oracle's partition:
+integer halo maps bit-exact, grad U / strain rate bit-exact, the rest <= 1e-11.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def build_parts(n_ranks, decomp):
+    from solidstateamfoam_b200 import cases
+    from solidstateamfoam_b200 import mesh as M
+    from solidstateamfoam_b200 import params as P
+
+    dims = (12, 10, 4 * n_ranks)
+    cell = 0.5e-3
+    box = ((0.0, 0.0, 0.0), (dims[0] * cell, dims[1] * cell, dims[2] * cell))
+    if decomp == "slab":
+        meshes = [M.hex_block(dims[0], dims[1], 4, (0, 0, r * 4 * cell), (dims[0] * cell, dims[1] * cell, 4 * cell),
+                              side_nbr_rank=tuple([-1] * 4 + [r - 1 if r > 0 else -1, r + 1 if r < n_ranks - 1 else -1]),
+                              my_rank=r) for r in range(n_ranks)]
+    else:
+        h = M.hex_block(*dims, length=(dims[0] * cell, dims[1] * cell, dims[2] * cell),
+                        affine=(1.0, 0.2, 0.1, 0.0, 1.0, 0.15, 0.0, 0.0, 1.0), _keep=True)
+        rng = np.random.default_rng(11)
+        nc = dims[0] * dims[1] * dims[2]
+        # blocky random partition: random owner per 2x2x2 brick -> ragged processor patches, every pair of ranks touches
+        ii, jj, kk = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij")
+        brick = (ii // 3) + 7 * (jj // 3) + 53 * (kk // 2)
+        owner_of_brick = rng.integers(0, n_ranks, size=brick.max() + 1)
+        cp = owner_of_brick[brick].transpose(2, 1, 0).reshape(-1)
+        _, meshes = M.decompose(h, cp, n_ranks)
+    parts = []
+    for r, m in enumerate(meshes):
+        top = m.patch_id("zmax")
+        mix = P.mixture(2700.0, 1.2, 896.0, 1005.0, P.k_cubic(100.0, 0.2, -1e-4, 1e-8, 293.0, 855.0), P.k_constant(0.026))
+        stick = P.constant_slip_stick(top, 0.9, 0.5, cases.OMEGA, 0.3)
+        rot = P.constant_rotational_slip(top, cases.OMEGA, 0.5, cases.VT)
+        flds = cases._fields(m, 777 + r, "tanh", box=box)
+        parts.append(cases._finish("mg", m, flds, cases.sheppard_wright_aa6061(), mix, stick, rot, 777))
+    return parts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--decomp", default="slab", choices=["slab", "random"])
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    from helpers import check_field, BIT_EXACT
+    from oracle import pyoracle as O
+    from solidstateamfoam_b200 import capi
+    from solidstateamfoam_b200 import params as P
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parts = build_parts(world, args.decomp)
+    # ---- oracle, all ranks in this process ----
+    ocs = []
+    for c in parts:
+        oc = O.OracleCase(c.mesh, c.patch_u_bc)
+        oc.set(P.F_U, c.U_i, c.U_b)
+        oc.set(P.F_T, c.T_i, c.T_b)
+        oc.set(P.F_ALPHA1, c.alpha1_i, c.alpha1_b)
+        oc.set(P.F_P, c.p_i, c.p_b)
+        oc.bc_rotational_slip(c.rotslip)
+        ocs.append(oc)
+    O.halo_exchange(ocs, P.F_T)
+    O.halo_exchange(ocs, P.F_ALPHA1)
+    O.update_multi(ocs, parts[0].params, form=O.FAITHFUL)
+    # ---- GPU, this rank's partition ----
+    case = parts[rank]
+    ctx = capi.Context(local)
+    uid = [capi.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0], rank, world)
+    ctx.load_case(case)
+    oc = ocs[rank]
+    for which in (P.ADDR_HALO_SEND_CELLS, P.ADDR_HALO_PATCH_OFFSETS, P.ADDR_EXTRA_FACE, P.ADDR_EXTRA_OTHER):
+        assert ctx.addressing(which).tobytes() == oc.addressing(which).tobytes(), P.ADDR_NAMES[which]
+    worst = 0.0
+    for variant in (0, 1):
+        ctx.set_cell_kernel(variant)
+        ctx.update_fused(case.params, capi.FUSED_HALO_INPUTS | capi.FUSED_WRITE_GRAD)
+        for f in case.outputs + [P.F_GRADU, P.F_U, P.F_T, P.F_ALPHA1]:
+            gi, gb = ctx.download(f)
+            w, _ = check_field(f"rank{rank} {P.FIELD_NAMES[f]}", np.concatenate([gi, gb]), oc.field(f), f in BIT_EXACT)
+            worst = max(worst, w)
+    c_gpu, a_gpu = ctx.friction_patch_centre()
+    c_ref, a_ref = oc.friction_patch_centre()
+    assert np.allclose(c_gpu, c_ref, rtol=1e-14, atol=0) and abs(a_gpu - a_ref) <= 1e-14 * a_ref
+    # staged path across ranks too
+    ctx.strain_rate(np.sqrt(2.0), P.F_STRAINRATE)
+    ctx.grad_u()
+    gi, gb = ctx.download(P.F_GRADU)
+    check_field("staged gradU", np.concatenate([gi, gb]), oc.field(P.F_GRADU), True)
+    n_proc = int(sum(case.mesh.patchSize[p] for p in range(case.mesh.nPatches) if case.mesh.patchKind[p] == 1))
+    dist.barrier()
+    print(f"[rank {rank}/{world}] {args.decomp}: {case.mesh.nCells} cells, {n_proc} processor faces, "
+          f"worst rel err {worst:.2e} -- OK", flush=True)
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
