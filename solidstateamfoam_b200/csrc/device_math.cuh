@@ -26,7 +26,8 @@ SSAM_DEV double ofMin(double a, double b) { return (a < b) ? a : b; }
 // bit-identical to the IEEE quotient the reference computes in k0*(T/T) and k*(T/T)
 // (incompressibleTwoPhaseThermalMixture.C:253,269).
 SSAM_DEV double selfRatio(double x) {
-    const bool ok = (x == x) && (x != 0.0) && (fabs(x) != __longlong_as_double(0x7ff0000000000000LL));
+    const unsigned h = unsigned(__double2hiint(x)) & 0x7fffffffu;  // integer pipe, not FP64
+    const bool ok = (h < 0x7ff00000u) && ((h | unsigned(__double2loint(x))) != 0u);
     return ok ? 1.0 : __longlong_as_double(0x7ff8000000000000LL);
 }
 

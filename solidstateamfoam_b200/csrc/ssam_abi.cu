@@ -34,6 +34,8 @@ struct ssam_ctx {
     int nExtra = 0;
     int4* tileDesc = nullptr;
     int nTiles = 0;
+    int pfDist = 148;    // L2 prefetch distance of the tiled kernel, in tiles (measured optimum, profiles/)
+    int bandwidthTiles = 0;  // ceil(max(neighbour - owner) / TILE)
     int cellKernel = 1;  // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged
     double *V = nullptr, *magSf_b = nullptr, *deltaCoeffs_b = nullptr;
     double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
@@ -240,6 +242,17 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
     CU(cudaMemcpyAsync(cursor, ctx->extraStart, (size_t(nc) + 1) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_extra_fill, gridFor(nF, 256), 256, ctx->owner, ctx->neighbour, ctx->bndFlags, nIF, nF, cursor, ctx->extra);
     LAUNCH(k_extra_sort, gridFor(nc, 256), 256, ctx->extraStart, nc, ctx->extra);
+    {
+        int* bw = nullptr;
+        TRY(devAlloc(ctx, &bw, 1));
+        CU(cudaMemsetAsync(bw, 0, sizeof(int), ctx->stream));
+        LAUNCH(k_bandwidth, gridFor(nIF, 256), 256, ctx->owner, ctx->neighbour, nIF, bw);
+        int h = 0;
+        CU(cudaMemcpyAsync(&h, bw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(bw);
+        ctx->bandwidthTiles = (h + TILE - 1) / TILE;
+    }
     ctx->nTiles = gridFor(nc, TILE);
     TRY(devAlloc(ctx, &ctx->tileDesc, size_t(ctx->nTiles)));
     LAUNCH(k_tile_desc, gridFor(ctx->nTiles, 256), 256, ctx->ownerStart, ctx->extraStart, nc, ctx->nTiles,
@@ -1050,6 +1063,9 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     a.prm = *p;
     a.d1 = deriveVisc(p->visc1);
     if (const char* dbg = std::getenv("SSAM_DBG")) a.dbg = std::atoi(dbg);
+    a.pfDist = ctx->pfDist;
+    if (const char* pf = std::getenv("SSAM_PF")) a.pfDist = std::atoi(pf);
+    a.pfDistU = a.pfDist + ctx->bandwidthTiles;
 
     if (ctx->nProcPatches && (flags & 2)) {
         TRY(haloExchangeField(ctx, SSAM_F_U));
