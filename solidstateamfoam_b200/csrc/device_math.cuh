@@ -61,6 +61,8 @@ struct ViscDerived {
     double mu0OverRho;  // mu0_/rho_                              NortonHoff.C:60
     double mMinus1;     // m_ - 1                                 NortonHoff.C:63
     double sqrt3;       // sqrt(3.0)                              NortonHoff.C:62
+    double invTmTa;     // 1/(Tm_ - Ta_): Th = (Tlim - Ta)*invTmTa differs from the quotient by <= 1 ulp
+    double invE0;       // 1/e0_
     int b2IsOne;        // pow(x, 1.0) == x exactly
     int invC2IsOne;
 };
@@ -77,11 +79,11 @@ SSAM_DEV double swAsinhOfLog(double t) {
 }
 SSAM_DEV ViscOut sheppardWright(const ssam_viscosity_params& p, const ViscDerived& d, double T, double e) {
     ViscOut o;
-    const double q = divExact(p.Q, p.R * T);  // Q_/(R_*temp_)  :64
+    const double q = divFast(p.Q, p.R * T);  // Q_/(R_*temp_)  :64
     const double qa = q - d.logA;
     o.sigmaf = p.sigmaR * swAsinhOfLog((fastLog(e) + qa) * d.invN);   // :74
     o.sigmay = p.sigmaR * swAsinhOfLog((d.log01 + qa) * d.invN);      // :91
-    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divExact(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :109-117
+    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divFast(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :109-117
     return o;
 }
 
@@ -89,16 +91,16 @@ SSAM_DEV ViscOut sheppardWright(const ssam_viscosity_params& p, const ViscDerive
 SSAM_DEV ViscOut fks(const ssam_viscosity_params& p, const ViscDerived& d, double T, double e) {
     ViscOut o;
     const double Tlim = ofMin(ofMax(T, p.Ta), p.Tm);                      // :108
-    const double Th = divExact(Tlim - p.Ta, d.TmTa);                      // :112
-    const double H = divExact(d.Hcoef * T, T);                            // :73  (X*T)/T, NaN at T = 0
+    const double Th = (Tlim - p.Ta) * d.invTmTa;                          // :112
+    const double H = d.Hcoef * selfRatio(T);                              // :73  (X*T)/T: X to 1 ulp, NaN at T = 0
     const double base = Th + kSMALL;
     const double pw = p.b1 * (d.b2IsOne ? base : fastPow(base, p.b2));    // :89 / :152
-    const double Lam = 1.0 + pw * (p.b3 * fastLog(divExact(e, p.e0) + kVSMALL));  // :89
-    const double z = 1.0 + fastExp(d.negC1 * Th);
-    const double Theta = 1.0 - divExact(1.0, d.invC2IsOne ? z : fastPow(z, d.invC2));  // :99
+    const double Lam = 1.0 + pw * (p.b3 * fastLog(e * d.invE0 + kVSMALL));  // :89
+    const double z = 1.0 + fastExp(d.negC1 * Th);                         // in (1, 2]
+    const double Theta = 1.0 - divFast(1.0, d.invC2IsOne ? z : fastPow(z, d.invC2));  // :99
     o.sigmaf = (H * Lam) * Theta;                                         // :129
     o.sigmay = (p.a1 * Theta) * (1.0 + pw * d.b3LogY);                    // :152
-    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divExact(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :172-181
+    o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divFast(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :172-181
     return o;
 }
 

@@ -51,6 +51,8 @@ struct ssam_ctx {
     int fricPatchCached = -1;
     double* fricSums = nullptr;  // device: [0..3] local sums, [4..7] cross-rank sums
     int qfricZeroedFor = -2;
+    bool nu2Filled = false;
+    double nu2FilledWith = 0.0;
 
     // halo
     int nProcPatches = 0, nProcFaces = 0;
@@ -183,6 +185,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->faceColour);
     c->fricPatchCached = -1;
     c->qfricZeroedFor = -2;
+    c->nu2Filled = false;
     c->haveMesh = false;
 }
 
@@ -325,6 +328,8 @@ ViscDerived deriveVisc(const ssam_viscosity_params& p) {
     d.mu0OverRho = p.mu0 / p.rho;
     d.mMinus1 = p.m - 1;
     d.sqrt3 = std::sqrt(3.0);
+    d.invTmTa = 1.0 / d.TmTa;
+    d.invE0 = 1.0 / p.e0;
     d.b2IsOne = (p.b2 == 1.0) ? 1 : 0;
     d.invC2IsOne = (d.invC2 == 1.0) ? 1 : 0;
     return d;
@@ -534,6 +539,7 @@ ssam_status viscosityCorrect(ssam_ctx* ctx, int phase, const ssam_viscosity_para
     }
     LAUNCH((k_map<ViscStage>), std::min(gridFor(ctx->nTot, 256), 148 * 32), 256, ctx->nTot, s);
     ctx->isSet[nuField] = true;
+    if (nuField == SSAM_F_NU2) ctx->nu2Filled = false;
     if (s.sigmaf) ctx->isSet[SSAM_F_SIGMAF] = ctx->isSet[SSAM_F_SIGMAY] = true;
     return SSAM_OK;
 }
@@ -853,6 +859,7 @@ ssam_status ssam_field_upload(ssam_ctx* ctx, int field, const double* internal, 
     }
     if (boundary) TRY(uploadAoS(ctx, boundary, ctx->nBnd, nc, ctx->plane[field], ctx->nCells));
     ctx->isSet[field] = true;
+    if (field == SSAM_F_NU2) ctx->nu2Filled = false;
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
@@ -875,6 +882,7 @@ ssam_status ssam_field_device_ptr(ssam_ctx* ctx, int field, int comp, void** ptr
     *ptr = ctx->plane[field][comp];
     if (len) *len = ctx->nTot;
     ctx->isSet[field] = true;  // the caller fills it on the device
+    if (field == SSAM_F_NU2) ctx->nu2Filled = false;
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
@@ -1067,6 +1075,13 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     if (const char* pf = std::getenv("SSAM_PF")) a.pfDist = std::atoi(pf);
     a.pfDistU = a.pfDist + ctx->bandwidthTiles;
 
+    // nu2 (Newtonian, constant): written only when the value changes or something else wrote the plane
+    if (!ctx->nu2Filled || ctx->nu2FilledWith != p->visc2.nu) {
+        FillStage fs{p->visc2.nu, ctx->plane[SSAM_F_NU2][0]};
+        LAUNCH((k_map<FillStage>), mapGrid(ctx), 256, ctx->nTot, fs);
+        ctx->nu2Filled = true;
+        ctx->nu2FilledWith = p->visc2.nu;
+    }
     if (ctx->nProcPatches && (flags & 2)) {
         TRY(haloExchangeField(ctx, SSAM_F_U));
         TRY(haloExchangeField(ctx, SSAM_F_T));

@@ -11,7 +11,7 @@ from helpers import ulp_diff
 
 pytestmark = pytest.mark.gpu
 
-LOG, EXP, POW, ASINH, DIVX, DIV, SELF, ASINH_EXP = range(8)
+LOG, EXP, POW, ASINH, DIVX, DIV, SELF, ASINH_EXP, DIVFAST = range(9)
 
 
 @pytest.fixture(scope="module")
@@ -57,6 +57,26 @@ def test_exact_division_is_ieee(ctx):
     assert np.array_equal(np.signbit(got[ok]), np.signbit(ref[ok]))
     # and the plain operator, for completeness
     assert np.array_equal(ctx.debug_math(DIV, A, B), ref, equal_nan=True)
+
+
+def test_fast_division(ctx):
+    """divFast: <= 2 ulp inside the guarded range, IEEE semantics for special divisors"""
+    r = rng()
+    n = 1_000_000
+    a = r.standard_normal(n) * 10.0 ** r.uniform(-100, 100, n)
+    b = r.standard_normal(n) * 10.0 ** r.uniform(-100, 100, n)
+    got = ctx.debug_math(DIVFAST, a, b)
+    assert ulp_diff(got, a / b).max() <= 2
+    s = special()
+    A, B = np.meshgrid(s, s)
+    A, B = A.ravel(), B.ravel()
+    with np.errstate(all="ignore"):
+        ref = A / B
+    got = ctx.debug_math(DIVFAST, A, B)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    fin = np.isfinite(ref) & (np.abs(ref) > 1e-300)
+    assert np.array_equal(got[~fin], ref[~fin], equal_nan=True) or np.allclose(got[~fin], ref[~fin], equal_nan=True)
+    assert ulp_diff(got[fin], ref[fin]).max() <= 2
 
 
 def test_self_ratio(ctx):
