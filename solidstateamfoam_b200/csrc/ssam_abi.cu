@@ -34,6 +34,10 @@ struct ssam_ctx {
     int nExtra = 0;
     int4* tileDesc = nullptr;
     int nTiles = 0;
+    int *tileListInterior = nullptr, *tileListCoupled = nullptr;
+    int nTilesInterior = 0, nTilesCoupled = 0;
+    cudaStream_t commStream = nullptr;
+    cudaEvent_t evMainToComm = nullptr, evCommToMain = nullptr;
     int pfDist = 148;    // L2 prefetch distance of the tiled kernel, in tiles (measured optimum, profiles/)
     int bandwidthTiles = 0;  // ceil(max(neighbour - owner) / TILE)
     int cellKernel = 1;  // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged
@@ -167,6 +171,8 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->extraStart);
     devFree(c->extra);
     devFree(c->tileDesc);
+    devFree(c->tileListInterior);
+    devFree(c->tileListCoupled);
     devFree(c->V);
     devFree(c->magSf_b);
     devFree(c->deltaCoeffs_b);
@@ -260,6 +266,29 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
     TRY(devAlloc(ctx, &ctx->tileDesc, size_t(ctx->nTiles)));
     LAUNCH(k_tile_desc, gridFor(ctx->nTiles, 256), 256, ctx->ownerStart, ctx->extraStart, nc, ctx->nTiles,
            ctx->tileDesc);
+    ctx->nTilesInterior = ctx->nTiles;
+    ctx->nTilesCoupled = 0;
+    if (ctx->nProcPatches > 0) {
+        // tiles that touch a processor patch wait for the halos; all others can start at once
+        int* flag = nullptr;
+        TRY(devAlloc(ctx, &flag, size_t(ctx->nTiles)));
+        LAUNCH(k_tile_coupled, ctx->nTiles, 128, ctx->extraStart, ctx->extra, nc, ctx->nTiles, flag);
+        std::vector<int> h(ctx->nTiles), li, lc;
+        CU(cudaMemcpyAsync(h.data(), flag, size_t(ctx->nTiles) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(flag);
+        for (int t = 0; t < ctx->nTiles; ++t) (h[t] ? lc : li).push_back(t);
+        ctx->nTilesInterior = int(li.size());
+        ctx->nTilesCoupled = int(lc.size());
+        TRY(devAlloc(ctx, &ctx->tileListInterior, li.size()));
+        TRY(devAlloc(ctx, &ctx->tileListCoupled, lc.size()));
+        if (!li.empty())
+            CU(cudaMemcpyAsync(ctx->tileListInterior, li.data(), li.size() * sizeof(int), cudaMemcpyHostToDevice,
+                               ctx->stream));
+        if (!lc.empty())
+            CU(cudaMemcpyAsync(ctx->tileListCoupled, lc.data(), lc.size() * sizeof(int), cudaMemcpyHostToDevice,
+                               ctx->stream));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(cursor);
     return SSAM_OK;
@@ -367,14 +396,26 @@ void fillMeshArgs(ssam_ctx* c, UpdateArgs& a) {
 }
 
 // ---- halo exchange --------------------------------------------------------------------------------------
-ssam_status haloExchangeField(ssam_ctx* ctx, int field) {
-    if (ctx->nProcPatches == 0) return SSAM_OK;
+// processorFvPatchField::evaluate for several fields at once: ONE pack kernel gathers field[faceCells] of
+// every processor patch for all component planes, ONE NCCL group sends each (patch, plane) run and
+// receives straight into the boundary part of the planes.
+ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cudaStream_t stream) {
+    if (ctx->nProcPatches == 0 || nFields == 0) return SSAM_OK;
     CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
-    TRY(ensureField(ctx, field));
-    const int nc = ncompOf(field);
-    const size_t needBuf = size_t(ctx->nProcFaces) * nc;
+    PlanePtrs pl;
+    int nc = 0;
+    for (int i = 0; i < nFields; ++i) {
+        TRY(ensureField(ctx, fields[i]));
+        for (int k = 0; k < ncompOf(fields[i]); ++k) {
+            CHECK(nc < 16, SSAM_ERR_INVALID, "too many component planes in one halo exchange");
+            pl.p[nc++] = ctx->plane[fields[i]][k];
+        }
+    }
+    for (int k = nc; k < 16; ++k) pl.p[k] = nullptr;
+    const size_t needBuf = size_t(ctx->nProcFaces) * 16;
     if (ctx->sendCap < needBuf) {
         CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->commStream) CU(cudaStreamSynchronize(ctx->commStream));
         devFree(ctx->sendBuf);
         TRY(devAlloc(ctx, &ctx->sendBuf, needBuf));
         ctx->sendCap = needBuf;
@@ -382,9 +423,10 @@ ssam_status haloExchangeField(ssam_ctx* ctx, int field) {
     HaloLayout L;
     L.nPatches = ctx->nProcPatches;
     for (int p = 0; p <= ctx->nProcPatches; ++p) L.offsets[p] = ctx->haloOffsets[p];
-    PlanePtrs pl;
-    for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? ctx->plane[field][k] : nullptr;
-    LAUNCH(k_halo_pack, gridFor((long long)ctx->nProcFaces * nc, 256), 256, ctx->haloSendCells, L, nc, pl, ctx->sendBuf);
+    k_halo_pack<<<gridFor((long long)ctx->nProcFaces * nc, 256), 256, 0, stream>>>(ctx->haloSendCells, L, nc, pl,
+                                                                                    ctx->sendBuf);
+    ctx->launches++;
+    CU(cudaGetLastError());
     NcclApi& N = nccl();
     NC(N.GroupStart());
     for (int p = 0; p < ctx->nProcPatches; ++p) {
@@ -393,14 +435,15 @@ ssam_status haloExchangeField(ssam_ctx* ctx, int field) {
         const int off = ctx->haloOffsets[p], np = ctx->haloOffsets[p + 1] - off;
         const int b0 = ctx->patchStart[patch] - ctx->nIF;
         for (int k = 0; k < nc; ++k) {
-            NC(N.Send(ctx->sendBuf + size_t(nc) * off + size_t(k) * np, np, ncclFloat64, peer, ctx->comm, ctx->stream));
-            NC(N.Recv(ctx->plane[field][k] + ctx->nCells + b0, np, ncclFloat64, peer, ctx->comm, ctx->stream));
+            NC(N.Send(ctx->sendBuf + size_t(nc) * off + size_t(k) * np, np, ncclFloat64, peer, ctx->comm, stream));
+            NC(N.Recv(pl.p[k] + ctx->nCells + b0, np, ncclFloat64, peer, ctx->comm, stream));
         }
     }
     NC(N.GroupEnd());
     ctx->launches++;  // one fused NCCL p2p kernel per group
     return SSAM_OK;
 }
+ssam_status haloExchangeField(ssam_ctx* ctx, int field) { return haloExchangeFields(ctx, &field, 1, ctx->stream); }
 
 ssam_status ensureFricSums(ssam_ctx* ctx, int patch) {
     if (ctx->fricPatchCached == patch) return SSAM_OK;
@@ -465,26 +508,36 @@ ssam_status launchCellsBoundary(ssam_ctx* ctx, const UpdateArgs& a, int model1, 
     return SSAM_OK;
 }
 
-template <int M>
-ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a) {
+template <int M, bool LIST>
+ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, int count, cudaStream_t stream) {
+    if (count == 0) return SSAM_OK;
+    UpdateArgs a = a0;
+    a.tileList = list;
+    a.tileCount = count;
     static bool configured = false;
     const int smem = int(sizeof(TileSmem));
     if (!configured) {
-        CU(cudaFuncSetAttribute(k_cells_tiled<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_cells_tiled<M, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    k_cells_tiled<M><<<ctx->nTiles, TILE, smem, ctx->stream>>>(a);
+    k_cells_tiled<M, LIST><<<count, TILE, smem, stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return SSAM_OK;
 }
-ssam_status launchCellsTiled(ssam_ctx* ctx, const UpdateArgs& a, int model1) {
+ssam_status launchCellsTiled(ssam_ctx* ctx, const UpdateArgs& a, int model1, const int* list, int count,
+                             cudaStream_t stream) {
+#define SSAM_TILED(M)                                                                   \
+    case M:                                                                             \
+        return list ? launchTiledOne<M, true>(ctx, a, list, count, stream)              \
+                    : launchTiledOne<M, false>(ctx, a, nullptr, count, stream);
     switch (model1) {
-        case SSAM_VISC_NEWTONIAN: return launchTiledOne<SSAM_VISC_NEWTONIAN>(ctx, a);
-        case SSAM_VISC_SHEPPARD_WRIGHT: return launchTiledOne<SSAM_VISC_SHEPPARD_WRIGHT>(ctx, a);
-        case SSAM_VISC_FKS: return launchTiledOne<SSAM_VISC_FKS>(ctx, a);
-        case SSAM_VISC_NORTON_HOFF: return launchTiledOne<SSAM_VISC_NORTON_HOFF>(ctx, a);
+        SSAM_TILED(SSAM_VISC_NEWTONIAN)
+        SSAM_TILED(SSAM_VISC_SHEPPARD_WRIGHT)
+        SSAM_TILED(SSAM_VISC_FKS)
+        SSAM_TILED(SSAM_VISC_NORTON_HOFF)
     }
+#undef SSAM_TILED
     return fail(ctx, SSAM_ERR_UNKNOWN_MODEL, "Unknown viscosityModel type");
 }
 
@@ -595,6 +648,9 @@ ssam_status ssam_destroy(ssam_ctx* ctx) {
     freeMesh(ctx);
     devFree(ctx->stage);
     devFree(ctx->fricSums);
+    if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
+    if (ctx->evMainToComm) cudaEventDestroy(ctx->evMainToComm);
+    if (ctx->evCommToMain) cudaEventDestroy(ctx->evCommToMain);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     delete ctx;
     return SSAM_OK;
@@ -1082,30 +1138,53 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         ctx->nu2Filled = true;
         ctx->nu2FilledWith = p->visc2.nu;
     }
-    if (ctx->nProcPatches && (flags & 2)) {
-        TRY(haloExchangeField(ctx, SSAM_F_U));
-        TRY(haloExchangeField(ctx, SSAM_F_T));
-        TRY(haloExchangeField(ctx, SSAM_F_ALPHA1));
+    // Multi-GPU schedule (tiled kernel):
+    //   main stream: interior tiles ------------------------------------------.
+    //   comm stream: pack + NCCL(U,temp,alpha1) -> coupled tiles -> pack + NCCL(epsilonDotEq[,...]) -+-> boundary faces
+    // so both halo exchanges and the tiles that need them hide behind the interior tiles.
+    const bool haloInputs = ctx->nProcPatches && (flags & 2);
+    const bool split = ctx->nProcPatches > 0 && ctx->cellKernel == 1;
+    if (ctx->nProcPatches && !ctx->commStream) {
+        // highest priority: the comm stream's small kernels must get SM slots as soon as CTAs of the
+        // interior-tile kernel retire, not after its whole grid has been dispatched
+        int prLo = 0, prHi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        CU(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, prHi));
+        CU(cudaEventCreateWithFlags(&ctx->evMainToComm, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->evCommToMain, cudaEventDisableTiming));
     }
+    int outs2[3], n2 = 0;
+    outs2[n2++] = SSAM_F_EPSDOT;
+    if (model1 == SSAM_VISC_NORTON_HOFF) outs2[n2++] = SSAM_F_STRAINRATE;
+    if (flags & 1) outs2[n2++] = SSAM_F_GRADU;
+    const int ins[3] = {SSAM_F_U, SSAM_F_T, SSAM_F_ALPHA1};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ctx->profile) {
         CU(cudaEventCreate(&ev0));
         CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, ctx->stream));
     }
-    if (ctx->cellKernel == 1) {
-        TRY(launchCellsTiled(ctx, a, model1));
+    if (split) {
+        CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->commStream, ctx->evMainToComm, 0));
+        if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->commStream));
+        TRY(launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream));
+        TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->commStream));
+        TRY(haloExchangeFields(ctx, outs2, n2, ctx->commStream));
+        CU(cudaEventRecord(ctx->evCommToMain, ctx->commStream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evCommToMain, 0));
     } else {
-        TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
+        if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->stream));
+        if (ctx->cellKernel == 1) {
+            TRY(launchCellsTiled(ctx, a, model1, nullptr, ctx->nTiles, ctx->stream));
+        } else {
+            TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
+        }
+        if (ctx->nProcPatches) TRY(haloExchangeFields(ctx, outs2, n2, ctx->stream));
     }
     if (ctx->profile) {
         CU(cudaEventRecord(ev1, ctx->stream));
         ctx->profEvents.emplace_back(ev0, ev1);
-    }
-    if (ctx->nProcPatches) {
-        TRY(haloExchangeField(ctx, SSAM_F_EPSDOT));
-        if (model1 == SSAM_VISC_NORTON_HOFF) TRY(haloExchangeField(ctx, SSAM_F_STRAINRATE));
-        if (flags & 1) TRY(haloExchangeField(ctx, SSAM_F_GRADU));
     }
     TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, true)));
     for (int f : outs) ctx->isSet[f] = true;
