@@ -272,6 +272,10 @@ typedef struct ssam_host_io {
     double* const* out_b;      /* [nOut] host boundary buffers (entries may be NULL) */
 } ssam_host_io;
 SSAM_API ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io);
+/* ssam_update_fused_host pipelines upload / cell kernel / download over contiguous chunks of tiles on three
+ * streams (PCIe is full duplex).  n < 0: automatic (default); 0 or 1: unpipelined; otherwise the requested
+ * number of chunks, reduced until a chunk is at least as deep as the mesh bandwidth. */
+SSAM_API ssam_status ssam_set_host_chunks(ssam_ctx* ctx, int n);
 
 /* ---- test hook ---------------------------------------------------------------------------------------
  * Evaluates one of the device math routines of csrc/fastmath.cuh on host arrays (tests/test_gpu_math.py):

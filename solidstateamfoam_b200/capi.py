@@ -23,7 +23,7 @@ SYMBOLS = [
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
     "ssam_solver_rho_rhocp", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
-    "ssam_update_fused_host", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
+    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
 ]
 
 
@@ -83,6 +83,7 @@ def load():
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
     L.ssam_update_fused_host.argtypes = [vp, C.POINTER(P.UpdateParams), C.POINTER(P.HostIO)]
+    L.ssam_set_host_chunks.argtypes = [vp, C.c_int]
     L.ssam_debug_math.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int64]
     L.ssam_comm_unique_id.argtypes = [vp]
     L.ssam_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
@@ -246,6 +247,9 @@ class Context:
     def update_fused(self, p: P.UpdateParams, flags: int = 0):
         self._chk(self.L.ssam_update_fused(self.h, C.byref(p), flags))
 
+    def set_host_chunks(self, n: int):
+        self._chk(self.L.ssam_set_host_chunks(self.h, n))
+
     def update_fused_host(self, p: P.UpdateParams, io: P.HostIO):
         self._chk(self.L.ssam_update_fused_host(self.h, C.byref(p), C.byref(io)))
 
@@ -276,6 +280,32 @@ class Context:
         for f in fields:
             mask |= 1 << f
         self._chk(self.L.ssam_halo_exchange(self.h, mask))
+
+    def host_update(self, case, out_fields, U_b=None):
+        """ssam_update_fused_host on numpy buffers: returns {field: (internal, boundary)}"""
+        n, nb = case.mesh.nCells, case.mesh.nBoundaryFaces
+        dp = C.POINTER(C.c_double)
+        keep = []
+
+        def ptr(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return a.ctypes.data_as(dp)
+
+        io = P.HostIO()
+        io.U_i, io.U_b = ptr(case.U_i), ptr(case.U_b if U_b is None else U_b)
+        io.T_i, io.T_b = ptr(case.T_i), ptr(case.T_b)
+        io.alpha1_i, io.alpha1_b = ptr(case.alpha1_i), ptr(case.alpha1_b)
+        io.p_i, io.p_b = ptr(case.p_i), ptr(case.p_b)
+        outs = list(out_fields)
+        oi = [np.empty(n) for _ in outs]
+        ob = [np.empty(max(nb, 1)) for _ in outs]
+        io.nOut = len(outs)
+        io.outFields = (C.c_int32 * len(outs))(*outs)
+        io.out_i = (dp * len(outs))(*[a.ctypes.data_as(dp) for a in oi])
+        io.out_b = (dp * len(outs))(*[a.ctypes.data_as(dp) for a in ob])
+        self.update_fused_host(case.params, io)
+        return {f: (oi[k], ob[k][:nb]) for k, f in enumerate(outs)}
 
     # convenience ----------------------------------------------------------------------------------
     def load_case(self, case, apply_bc=True):

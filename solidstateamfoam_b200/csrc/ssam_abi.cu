@@ -36,10 +36,14 @@ struct ssam_ctx {
     int nTiles = 0;
     int *tileListInterior = nullptr, *tileListCoupled = nullptr;
     int nTilesInterior = 0, nTilesCoupled = 0;
+    int* tileIota = nullptr;  // identity tile list (chunked launches of the host-staged pipeline)
+    cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaStream_t commStream = nullptr;
     cudaEvent_t evMainToComm = nullptr, evCommToMain = nullptr;
     int pfDist = 148;    // L2 prefetch distance of the tiled kernel, in tiles (measured optimum, profiles/)
     int bandwidthTiles = 0;  // ceil(max(neighbour - owner) / TILE)
+    int hostChunks = -1;  // >= 0 overrides the chunk count of the host-staged pipeline (0/1 = unpipelined)
+    int nTilesOversize = 0;
     int cellKernel = 1;  // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged
     double *V = nullptr, *magSf_b = nullptr, *deltaCoeffs_b = nullptr;
     double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
@@ -171,6 +175,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->extraStart);
     devFree(c->extra);
     devFree(c->tileDesc);
+    devFree(c->tileIota);
     devFree(c->tileListInterior);
     devFree(c->tileListCoupled);
     devFree(c->V);
@@ -266,6 +271,13 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
     TRY(devAlloc(ctx, &ctx->tileDesc, size_t(ctx->nTiles)));
     LAUNCH(k_tile_desc, gridFor(ctx->nTiles, 256), 256, ctx->ownerStart, ctx->extraStart, nc, ctx->nTiles,
            ctx->tileDesc);
+    {
+        std::vector<int> iota(ctx->nTiles);
+        for (int t = 0; t < ctx->nTiles; ++t) iota[t] = t;
+        TRY(devAlloc(ctx, &ctx->tileIota, iota.size()));
+        CU(cudaMemcpyAsync(ctx->tileIota, iota.data(), iota.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->nTilesInterior = ctx->nTiles;
     ctx->nTilesCoupled = 0;
     if (ctx->nProcPatches > 0) {
@@ -303,7 +315,7 @@ ssam_status uploadAoS(ssam_ctx* ctx, const double* host, int n, int nc, double* 
     TRY(ensureStage(ctx, size_t(n) * nc));
     CU(cudaMemcpyAsync(ctx->stage, host, size_t(n) * nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PlanePtrs pl;
-    for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
+    for (int k = 0; k < 16; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
     LAUNCH(k_aos_to_soa_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset);
     return SSAM_OK;
 }
@@ -316,7 +328,7 @@ ssam_status downloadAoS(ssam_ctx* ctx, double* host, int n, int nc, double* cons
     }
     TRY(ensureStage(ctx, size_t(n) * nc));
     PlanePtrs pl;
-    for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
+    for (int k = 0; k < 16; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
     LAUNCH(k_soa_to_aos_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset);
     CU(cudaMemcpyAsync(host, ctx->stage, size_t(n) * nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     // the staging buffer is reused by the next transfer
@@ -648,6 +660,8 @@ ssam_status ssam_destroy(ssam_ctx* ctx) {
     freeMesh(ctx);
     devFree(ctx->stage);
     devFree(ctx->fricSums);
+    if (ctx->h2dStream) cudaStreamDestroy(ctx->h2dStream);
+    if (ctx->d2hStream) cudaStreamDestroy(ctx->d2hStream);
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->evMainToComm) cudaEventDestroy(ctx->evMainToComm);
     if (ctx->evCommToMain) cudaEventDestroy(ctx->evCommToMain);
@@ -678,6 +692,12 @@ ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking) {
 }
 
 int64_t ssam_launch_count(const ssam_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+ssam_status ssam_set_host_chunks(ssam_ctx* ctx, int n) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    ctx->hostChunks = n;
+    return SSAM_OK;
+}
 
 ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant) {
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
@@ -1081,7 +1101,15 @@ ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* 
 }
 
 // ---- fused update ---------------------------------------------------------------------------------------------
-static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, int flags) {
+// Host-staged pipeline (ssam_update_fused_host): the cell kernel runs chunk by chunk (contiguous tile
+// ranges); chunk k starts when the inputs of chunks <= k+1 have landed and signals evOut[k] when done.
+struct ChunkPlan {
+    int nChunks = 0, tilesPerChunk = 0;
+    std::vector<cudaEvent_t> evIn, evOut;
+};
+
+static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, int flags,
+                                    const ChunkPlan* plan = nullptr) {
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     TRY(checkViscModel(ctx, &p->visc1));
     TRY(checkViscModel(ctx, &p->visc2));
@@ -1175,7 +1203,14 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         CU(cudaStreamWaitEvent(ctx->stream, ctx->evCommToMain, 0));
     } else {
         if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->stream));
-        if (ctx->cellKernel == 1) {
+        if (plan) {
+            for (int k = 0; k < plan->nChunks; ++k) {
+                const int t0 = k * plan->tilesPerChunk, t1 = std::min(ctx->nTiles, t0 + plan->tilesPerChunk);
+                CU(cudaStreamWaitEvent(ctx->stream, plan->evIn[std::min(k + 1, plan->nChunks - 1)], 0));
+                TRY(launchCellsTiled(ctx, a, model1, ctx->tileIota + t0, t1 - t0, ctx->stream));
+                CU(cudaEventRecord(plan->evOut[k], ctx->stream));
+            }
+        } else if (ctx->cellKernel == 1) {
             TRY(launchCellsTiled(ctx, a, model1, nullptr, ctx->nTiles, ctx->stream));
         } else {
             TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
@@ -1200,9 +1235,7 @@ ssam_status ssam_update_fused(ssam_ctx* ctx, const ssam_update_params* p, int fl
     return finish(ctx);
 }
 
-ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io) {
-    CHECK(ctx && p && io, SSAM_ERR_INVALID, "null argument");
-    CHECK(io->U_i && io->T_i && io->alpha1_i, SSAM_ERR_INVALID, "U, temp and alpha1 host buffers are required");
+static ssam_status updateFusedHostSimple(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io) {
     struct In {
         int f;
         const double *i, *b;
@@ -1223,7 +1256,7 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
             CU(cudaMemcpyAsync(ctx->stage, in.i, size_t(ctx->nCells) * nc * sizeof(double), cudaMemcpyHostToDevice,
                                ctx->stream));
             PlanePtrs pl;
-            for (int k = 0; k < 9; ++k) pl.p[k] = k < nc ? ctx->plane[in.f][k] : nullptr;
+            for (int k = 0; k < 16; ++k) pl.p[k] = k < nc ? ctx->plane[in.f][k] : nullptr;
             LAUNCH(k_aos_to_soa_n, gridFor((long long)ctx->nCells * nc, 256), 256, ctx->stage, ctx->nCells, nc, pl, 0);
             if (in.b && ctx->nBnd) {
                 double* st2 = ctx->stage + size_t(ctx->nCells) * nc;
@@ -1238,7 +1271,6 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
     TRY(updateFusedAsync(ctx, p, ctx->nProcPatches ? 2 : 0));
     for (int o = 0; o < io->nOut; ++o) {
         const int f = io->outFields[o];
-        CHECK(f >= 0 && f < SSAM_F_COUNT && ncompOf(f) == 1, SSAM_ERR_INVALID, "host outputs must be scalar fields");
         TRY(need(ctx, f, "requested output was not produced by this update"));
         if (io->out_i && io->out_i[o])
             CU(cudaMemcpyAsync(io->out_i[o], ctx->plane[f][0], size_t(ctx->nCells) * sizeof(double),
@@ -1249,6 +1281,126 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
     }
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
+}
+
+// Pipelined variant (single GPU, tiled kernel): PCIe is full duplex, so the upload of chunk k+2's
+// inputs, the cell kernel on chunk k+1 and the download of chunk k's outputs run concurrently on three
+// streams.  The gather of a chunk reaches at most `bandwidthTiles` tiles ahead, hence the k+1 dependency.
+static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io,
+                                            int nChunks) {
+    if (!ctx->h2dStream) {
+        CU(cudaStreamCreateWithFlags(&ctx->h2dStream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->d2hStream, cudaStreamNonBlocking));
+    }
+    ChunkPlan plan;
+    plan.nChunks = nChunks;
+    plan.tilesPerChunk = (ctx->nTiles + nChunks - 1) / nChunks;
+    plan.evIn.resize(nChunks);
+    plan.evOut.resize(nChunks);
+    for (int k = 0; k < nChunks; ++k) {
+        CU(cudaEventCreateWithFlags(&plan.evIn[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&plan.evOut[k], cudaEventDisableTiming));
+    }
+    cudaEvent_t evStart, evTail;
+    CU(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&evTail, cudaEventDisableTiming));
+    const int fIn[4] = {SSAM_F_U, SSAM_F_T, SSAM_F_ALPHA1, SSAM_F_P};
+    const double* hi[4] = {io->U_i, io->T_i, io->alpha1_i, io->p_i};
+    const double* hb[4] = {io->U_b, io->T_b, io->alpha1_b, io->p_b};
+    for (int i = 0; i < 4; ++i)
+        if (hi[i]) TRY(ensureField(ctx, fIn[i]));
+    const size_t chunkCells = size_t(plan.tilesPerChunk) * TILE;
+    TRY(ensureStage(ctx, std::max(size_t(ctx->nBnd) * 3, 2 * chunkCells * 3)));
+    // order the copy streams after whatever the caller queued on the compute stream
+    CU(cudaEventRecord(evStart, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->h2dStream, evStart, 0));
+    CU(cudaStreamWaitEvent(ctx->d2hStream, evStart, 0));
+    cudaStream_t keep = ctx->stream;
+    // boundary parts first (small), on the upload stream
+    ctx->stream = ctx->h2dStream;
+    ssam_status st = SSAM_OK;
+    for (int i = 0; i < 4 && st == SSAM_OK; ++i)
+        if (hi[i] && hb[i] && ctx->nBnd)
+            st = uploadAoS(ctx, hb[i], ctx->nBnd, ncompOf(fIn[i]), ctx->plane[fIn[i]], ctx->nCells);
+    PlanePtrs plU;
+    for (int k = 0; k < 16; ++k) plU.p[k] = k < 3 ? ctx->plane[SSAM_F_U][k] : nullptr;
+    for (int k = 0; k < nChunks && st == SSAM_OK; ++k) {
+        const int c0 = int(std::min(size_t(ctx->nCells), size_t(k) * chunkCells));
+        const int c1 = int(std::min(size_t(ctx->nCells), size_t(k + 1) * chunkCells));
+        const int n = c1 - c0;
+        if (n > 0) {
+            double* stg = ctx->stage + size_t(k & 1) * chunkCells * 3;
+            cudaMemcpyAsync(stg, io->U_i + size_t(c0) * 3, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                            ctx->h2dStream);
+            k_aos_to_soa_n<<<gridFor((long long)n * 3, 256), 256, 0, ctx->h2dStream>>>(stg, n, 3, plU, c0);
+            ctx->launches++;
+            for (int i = 1; i < 4; ++i)
+                if (hi[i])
+                    cudaMemcpyAsync(ctx->plane[fIn[i]][0] + c0, hi[i] + c0, size_t(n) * sizeof(double),
+                                    cudaMemcpyHostToDevice, ctx->h2dStream);
+        }
+        if (cudaEventRecord(plan.evIn[k], ctx->h2dStream) != cudaSuccess) st = SSAM_ERR_CUDA;
+    }
+    ctx->stream = keep;
+    if (st != SSAM_OK) return fail(ctx, st, "host-staged pipeline: upload failed");
+    for (int i = 0; i < 4; ++i)
+        if (hi[i]) ctx->isSet[fIn[i]] = true;
+    // the compute stream must not start before the boundary values are there: evIn[0] is recorded after them
+    CU(cudaStreamWaitEvent(ctx->stream, plan.evIn[0], 0));
+    TRY(updateFusedAsync(ctx, p, 0, &plan));
+    CU(cudaEventRecord(evTail, ctx->stream));
+    // downloads: internal parts chunk by chunk as the cell kernel finishes them (qfric and the boundary
+    // parts are final only after the boundary / friction kernels, i.e. after evTail)
+    for (int k = 0; k < nChunks; ++k) {
+        const int c0 = int(std::min(size_t(ctx->nCells), size_t(k) * chunkCells));
+        const int c1 = int(std::min(size_t(ctx->nCells), size_t(k + 1) * chunkCells));
+        if (c1 <= c0) continue;
+        CU(cudaStreamWaitEvent(ctx->d2hStream, plan.evOut[k], 0));
+        for (int o = 0; o < io->nOut; ++o) {
+            const int f = io->outFields[o];
+            if (f == SSAM_F_QFRIC || !(io->out_i && io->out_i[o])) continue;
+            TRY(need(ctx, f, "requested output was not produced by this update"));
+            CU(cudaMemcpyAsync(io->out_i[o] + c0, ctx->plane[f][0] + c0, size_t(c1 - c0) * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->d2hStream));
+        }
+    }
+    CU(cudaStreamWaitEvent(ctx->d2hStream, evTail, 0));
+    for (int o = 0; o < io->nOut; ++o) {
+        const int f = io->outFields[o];
+        TRY(need(ctx, f, "requested output was not produced by this update"));
+        if (f == SSAM_F_QFRIC && io->out_i && io->out_i[o])
+            CU(cudaMemcpyAsync(io->out_i[o], ctx->plane[f][0], size_t(ctx->nCells) * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->d2hStream));
+        if (io->out_b && io->out_b[o] && ctx->nBnd)
+            CU(cudaMemcpyAsync(io->out_b[o], ctx->plane[f][0] + ctx->nCells, size_t(ctx->nBnd) * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->d2hStream));
+    }
+    CU(cudaStreamSynchronize(ctx->d2hStream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->h2dStream));
+    for (int k = 0; k < nChunks; ++k) {
+        cudaEventDestroy(plan.evIn[k]);
+        cudaEventDestroy(plan.evOut[k]);
+    }
+    cudaEventDestroy(evStart);
+    cudaEventDestroy(evTail);
+    return SSAM_OK;
+}
+
+ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io) {
+    CHECK(ctx && p && io, SSAM_ERR_INVALID, "null argument");
+    CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    CHECK(io->U_i && io->T_i && io->alpha1_i, SSAM_ERR_INVALID, "U, temp and alpha1 host buffers are required");
+    for (int o = 0; o < io->nOut; ++o)
+        CHECK(io->outFields[o] >= 0 && io->outFields[o] < SSAM_F_COUNT && ncompOf(io->outFields[o]) == 1,
+              SSAM_ERR_INVALID, "host outputs must be scalar fields");
+    // chunks of >= 1024 tiles, each at least as deep as the mesh bandwidth (so a chunk only gathers from
+    // itself and its two neighbours)
+    int nChunks = ctx->hostChunks >= 0 ? std::min(ctx->hostChunks, 64) : std::min(16, ctx->nTiles / 1024);
+    while (nChunks > 1 && (ctx->nTiles + nChunks - 1) / nChunks < ctx->bandwidthTiles + 1) --nChunks;
+    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel == 1 && ctx->nTilesOversize == 0)
+        return updateFusedHostPipelined(ctx, p, io, nChunks);
+    return updateFusedHostSimple(ctx, p, io);
 }
 
 // ---- device-math evaluation (tests) -----------------------------------------------------------------------------

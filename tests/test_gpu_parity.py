@@ -215,3 +215,26 @@ def test_edge_values(ctx):
     compare_ctx_oracle(ctx, oc, case.outputs)
     ki, _ = ctx.download(P.F_K)
     assert np.isnan(ki[6]) and np.isnan(oc.field(P.F_K)[6])
+
+
+@pytest.mark.parametrize("chunks", [0, 3, 7])
+def test_host_staged_update_equals_device_resident(ctx, chunks):
+    """ssam_update_fused_host (the e2e path): plain and pipelined over chunks, bit-identical to the
+    device-resident update on the same inputs"""
+    case = cases.cfg2(dims=(64, 32, 24))  # 192 tiles, bandwidth 8 tiles
+    ctx.load_case(case)
+    ctx.update_fused(case.params, 0)
+    ref = {f: ctx.download(f) for f in case.outputs}
+    U_i, U_b = ctx.download(P.F_U)
+    ctx.set_host_chunks(chunks)
+    try:
+        # scribble over the device inputs first: the host path must bring its own
+        z = np.zeros(case.mesh.nCells)
+        ctx.upload(P.F_T, z + 1.0, None)
+        ctx.upload(P.F_ALPHA1, z, None)
+        got = ctx.host_update(case, case.outputs, U_b=U_b)
+    finally:
+        ctx.set_host_chunks(-1)
+    for f in case.outputs:
+        assert np.array_equal(got[f][0], ref[f][0], equal_nan=True), (chunks, P.FIELD_NAMES[f])
+        assert np.array_equal(got[f][1], ref[f][1], equal_nan=True), (chunks, P.FIELD_NAMES[f] + " boundary")
