@@ -36,6 +36,7 @@ struct ssam_ctx {
     int nTiles = 0;
     int *tileListInterior = nullptr, *tileListCoupled = nullptr;
     int nTilesInterior = 0, nTilesCoupled = 0;
+    int* tileOrder = nullptr;  // L2-friendly traversal order of the tiles (nullptr = natural order)
     int* tileIota = nullptr;  // identity tile list (chunked launches of the host-staged pipeline)
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaStream_t commStream = nullptr;
@@ -176,6 +177,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->extra);
     devFree(c->tileDesc);
     devFree(c->tileIota);
+    devFree(c->tileOrder);
     devFree(c->tileListInterior);
     devFree(c->tileListCoupled);
     devFree(c->V);
@@ -260,7 +262,7 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
         int* bw = nullptr;
         TRY(devAlloc(ctx, &bw, 1));
         CU(cudaMemsetAsync(bw, 0, sizeof(int), ctx->stream));
-        LAUNCH(k_bandwidth, gridFor(nIF, 256), 256, ctx->owner, ctx->neighbour, nIF, bw);
+        LAUNCH(k_bandwidth, std::min(gridFor(nIF, 256), 148 * 8), 256, ctx->owner, ctx->neighbour, nIF, bw);
         int h = 0;
         CU(cudaMemcpyAsync(&h, bw, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -611,6 +613,48 @@ ssam_status viscosityCorrect(ssam_ctx* ctx, int phase, const ssam_viscosity_para
 
 int mapGrid(const ssam_ctx* c) { return std::min(gridFor(c->nTot, 256), 148 * 32); }
 
+// Traversal order of the tiles.  The cell kernel re-reads, from L2, the face records and U values that the
+// tile `bandwidth` cells earlier brought in; in natural order that reuse distance is the cell bandwidth
+// of the mesh (nx*ny cells on a blockMesh box: 70 MB of traffic for a 512x512 plane, more than L2 keeps).
+// A breadth-first (Cuthill-McKee) order of the tile graph walks the mesh in wavefronts, which cuts the
+// reuse distance to one wavefront.  Pure integer preprocessing on the host arrays; cells and faces are NOT
+// renumbered, so the per-cell summation order - and with it every result bit - is unchanged.
+ssam_status buildTileOrder(ssam_ctx* ctx, const ssam_mesh_desc* m) {
+    devFree(ctx->tileOrder);
+    const long long reuseBytes = (long long)ctx->bandwidthTiles * TILE * 270;
+    if (reuseBytes < (40ll << 20) || ctx->nTiles < 4) return SSAM_OK;  // natural order already fits L2
+    const int nT = ctx->nTiles;
+    std::vector<std::vector<int>> adj(nT);
+    for (int f = 0; f < m->nInternalFaces; ++f) {
+        const int ta = m->owner[f] / TILE, tb = m->neighbour[f] / TILE;
+        if (ta == tb) continue;
+        if (adj[ta].empty() || adj[ta].back() != tb) adj[ta].push_back(tb);
+        if (adj[tb].empty() || adj[tb].back() != ta) adj[tb].push_back(ta);
+    }
+    for (auto& v : adj) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+    }
+    std::vector<int> order;
+    order.reserve(nT);
+    std::vector<char> seen(nT, 0);
+    for (int root = 0; root < nT; ++root) {
+        if (seen[root]) continue;
+        seen[root] = 1;
+        order.push_back(root);
+        for (size_t head = order.size() - 1; head < order.size(); ++head)
+            for (int t : adj[order[head]])
+                if (!seen[t]) {
+                    seen[t] = 1;
+                    order.push_back(t);
+                }
+    }
+    TRY(devAlloc(ctx, &ctx->tileOrder, size_t(nT)));
+    CU(cudaMemcpyAsync(ctx->tileOrder, order.data(), size_t(nT) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
 ssam_status mixtureCalcNu(ssam_ctx* ctx, const ssam_mixture_params* p) {
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(need(ctx, SSAM_F_NU1, "nu1"));
@@ -818,6 +862,7 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
                            size_t(ctx->patchSize[patch]) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     }
     TRY(buildAddressing(ctx));
+    if (ctx->nProcPatches == 0) TRY(buildTileOrder(ctx, m));
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
@@ -1211,7 +1256,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
                 CU(cudaEventRecord(plan->evOut[k], ctx->stream));
             }
         } else if (ctx->cellKernel == 1) {
-            TRY(launchCellsTiled(ctx, a, model1, nullptr, ctx->nTiles, ctx->stream));
+            TRY(launchCellsTiled(ctx, a, model1, ctx->tileOrder, ctx->nTiles, ctx->stream));
         } else {
             TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
         }
