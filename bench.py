@@ -263,12 +263,17 @@ def run_gpu(args):
     cells_ms, cells_n = ctx.profile_get()
     ctx.profile_enable(False)
     # the timed region lasts a few tens of ms, too short for nvidia-smi's sampling period: keep the very
-    # same step running for ~1 s more so the clock record describes the GPU under this load
-    t_end = time.time() + 1.0
-    while time.time() < t_end:
-        for _ in range(20):
-            ctx.update_fused(case.params, flags)
-        torch.cuda.synchronize()
+    # same step running for ~1 s more so the clock record describes the GPU under this load.  The number
+    # of extra steps must be identical on every rank (each step is a collective exchange when N > 1).
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if n_ranks > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    n_extra = int(min(5000, max(20, 1000.0 / max(float(tmax.item()) / args.steps, 1e-3))))
+    for i in range(n_extra):
+        ctx.update_fused(case.params, flags)
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "timed region + 1 s of the same step repeated"
