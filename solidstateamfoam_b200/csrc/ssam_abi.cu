@@ -528,11 +528,11 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
     UpdateArgs a = a0;
     a.tileList = list;
     a.tileCount = count;
-    static bool configured = false;
+    static bool configured[64] = {false};  // per device: the attribute belongs to the device's context
     const int smem = int(sizeof(TileSmem));
-    if (!configured) {
+    if (!configured[ctx->device & 63]) {
         CU(cudaFuncSetAttribute(k_cells_tiled<M, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured[ctx->device & 63] = true;
     }
     k_cells_tiled<M, LIST><<<count, TILE, smem, stream>>>(a);
     ctx->launches++;
@@ -1199,7 +1199,6 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     a.qvisc = ctx->plane[SSAM_F_QVISC][0];
     a.prm = *p;
     a.d1 = deriveVisc(p->visc1);
-    if (const char* dbg = std::getenv("SSAM_DBG")) a.dbg = std::atoi(dbg);
     a.pfDist = ctx->pfDist;
     if (const char* pf = std::getenv("SSAM_PF")) a.pfDist = std::atoi(pf);
     a.pfDistU = a.pfDist + ctx->bandwidthTiles;

@@ -238,3 +238,18 @@ def test_host_staged_update_equals_device_resident(ctx, chunks):
     for f in case.outputs:
         assert np.array_equal(got[f][0], ref[f][0], equal_nan=True), (chunks, P.FIELD_NAMES[f])
         assert np.array_equal(got[f][1], ref[f][1], equal_nan=True), (chunks, P.FIELD_NAMES[f] + " boundary")
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 1), (2, 1, 1), (1, 1, 3), (257, 1, 1), (3, 2, 1)])
+def test_degenerate_meshes(ctx, dims):
+    """one cell (no internal face), one row crossing a tile boundary, single layers"""
+    case = cases.cfg1(dims=dims)
+    for variant in (0, 1):
+        ctx.load_case(case)
+        ctx.set_cell_kernel(variant)
+        ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+        oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
+        compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU])
+        for which in (P.ADDR_OWNER_START, P.ADDR_EXTRA_START, P.ADDR_EXTRA_FACE, P.ADDR_CELL_FACES, P.ADDR_FACE_COLOUR):
+            assert ctx.addressing(which).tobytes() == oc.addressing(which).tobytes()
+    ctx.set_cell_kernel(1)
