@@ -73,7 +73,7 @@ def build_meshgen(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, "libssam_meshgen.so")
     src = os.path.join(PKG, "meshgen", "meshgen.cpp")
-    if not force and _newer(target, [src]):
+    if not force and _newer(target, [src, os.path.join(PKG, "meshgen", "foam_io.inc")]):
         return target
     _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", target, src], verbose)
     return target

@@ -283,6 +283,41 @@ def write_case_dir(path: str, case: Case, eps0: float = 1.0, mu0: float = 1.0) -
                      (np.full(m.nCells, eps0), np.full(nb, eps0)), (np.full(m.nCells, mu0), np.full(nb, mu0))):
             np.ascontiguousarray(i, dtype=np.float64).tofile(fh)
             np.ascontiguousarray(b, dtype=np.float64).tofile(fh)
+    _write_dicts(path, case)
+
+
+def write_foam_case(path: str, case: Case, handle, binary: bool = False) -> None:
+    """The same case as a real OpenFOAM case directory: constant/polyMesh, 0/{U,temp,alpha.metal,p} and the
+    dictionaries (`handle` = mesh.MeshHandle of the case's hex block, which carries points and faces)."""
+    import os
+
+    handle.write_polymesh(os.path.join(path, "constant", "polyMesh"), binary=binary)
+    _write_dicts(path, case)
+    u_path = os.path.join(path, "0", "U")
+    bc_text = open(u_path).read()  # the rotational-slip patch entry written by _write_dicts
+    handle.write_field(u_path, "U", case.U_i, case.U_b, case.patch_u_bc, binary)
+    # splice the BC entry of the tool patch into the field file (type + parameters; value stays)
+    if case.rotslip is not None:
+        pname = case.mesh.patchName[case.rotslip.patch]
+        entry = bc_text[bc_text.index(pname):]
+        entry = entry[entry.index("{") + 1:entry.index("}")]
+        params = "\n".join(l for l in entry.splitlines() if l.strip() and not l.strip().startswith("value"))
+        txt = open(u_path, "rb").read()
+        marker = (f"    {pname}\n    {{\n        type            fixedValue;\n").encode()
+        assert marker in txt
+        txt = txt.replace(marker, (f"    {pname}\n    {{\n" + params + "\n").encode())
+        open(u_path, "wb").write(txt)
+    handle.write_field(os.path.join(path, "0", "temp"), "temp", case.T_i, case.T_b, None, binary)
+    handle.write_field(os.path.join(path, "0", "alpha.metal"), "alpha.metal", case.alpha1_i, case.alpha1_b, None, binary)
+    handle.write_field(os.path.join(path, "0", "p"), "p", case.p_i, case.p_b, None, binary)
+
+
+def _write_dicts(path: str, case: Case) -> None:
+    import os
+
+    m = case.mesh
+    os.makedirs(os.path.join(path, "constant"), exist_ok=True)
+    os.makedirs(os.path.join(path, "0"), exist_ok=True)
     p = case.params
     with open(os.path.join(path, "constant", "transportProperties"), "w") as fh:
         fh.write("// written by solidstateamfoam_b200.cases.write_case_dir\nphases (metal air);\n\nmetal\n{\n")

@@ -48,6 +48,17 @@ def _meshgen():
         lib.smg_patch_name.argtypes = [P, C.c_int]
         lib.smg_has_global_maps.restype = C.c_int32
         lib.smg_has_global_maps.argtypes = [P]
+        lib.smg_points.restype = dp
+        lib.smg_points.argtypes = [P]
+        lib.smg_n_points.restype = C.c_int64
+        lib.smg_n_points.argtypes = [P]
+        lib.smg_write_polymesh.argtypes = [P, C.c_char_p, C.c_int]
+        lib.smg_read_polymesh.restype = P
+        lib.smg_read_polymesh.argtypes = [C.c_char_p]
+        lib.smg_couple_processor_patches.argtypes = [C.POINTER(P), C.c_int]
+        lib.smg_write_field.argtypes = [P, C.c_char_p, C.c_char_p, C.c_int, dp, dp, ip, C.c_int]
+        lib.smg_read_field.argtypes = [P, C.c_char_p, C.c_int, dp, dp, ip]
+        lib.smg_io_error.restype = C.c_char_p
         _lib = lib
     return _lib
 
@@ -205,3 +216,85 @@ def slab_partition(nx, ny, nz_per_rank, rank, n_ranks, origin=(0.0, 0.0, 0.0), c
                   side_nbr_rank=side, my_rank=rank)
     m.meta.update(rank=rank, n_ranks=n_ranks)
     return m
+
+
+# ---- OpenFOAM case I/O ------------------------------------------------------------
+class FoamIOError(RuntimeError):
+    pass
+
+
+class MeshHandle:
+    """A mesh kept alive on the C++ side (needed for polyMesh / field I/O, which uses points and faces)."""
+
+    def __init__(self, h):
+        if not h:
+            raise FoamIOError(_meshgen().smg_io_error().decode())
+        self.h = C.c_void_p(h) if not isinstance(h, C.c_void_p) else h
+
+    def mesh(self) -> Mesh:
+        return _from_handle(self.h, free=False)
+
+    def close(self):
+        if self.h:
+            _meshgen().smg_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def write_polymesh(self, polymesh_dir: str, binary: bool = False):
+        if _meshgen().smg_write_polymesh(self.h, polymesh_dir.encode(), 1 if binary else 0):
+            raise FoamIOError(_meshgen().smg_io_error().decode())
+
+    def write_field(self, path: str, name: str, internal, boundary, patch_bc=None, binary: bool = False):
+        i = np.ascontiguousarray(internal, dtype=np.float64)
+        b = np.ascontiguousarray(boundary, dtype=np.float64)
+        nc = 1 if i.ndim == 1 else i.shape[1]
+        bc = None
+        if patch_bc is not None:
+            bca = np.ascontiguousarray(patch_bc, dtype=np.int32)
+            bc = bca.ctypes.data_as(C.POINTER(C.c_int32))
+        dp = C.POINTER(C.c_double)
+        if _meshgen().smg_write_field(self.h, path.encode(), name.encode(), nc, i.ctypes.data_as(dp),
+                                      b.ctypes.data_as(dp), bc, 1 if binary else 0):
+            raise FoamIOError(_meshgen().smg_io_error().decode())
+
+    def read_field(self, path: str, ncomp: int):
+        """(internal, boundary, patch_bc) of a volScalarField / volVectorField file; zeroGradient patches are
+        evaluated (value = adjacent cell), patch_bc: 0 value-type, 1 zeroGradient."""
+        lib = _meshgen()
+        sz = (C.c_int32 * 4)()
+        lib.smg_sizes(self.h, sz)
+        nc, nif, nf, npch = (int(v) for v in sz)
+        shape_i = (nc, ncomp) if ncomp > 1 else (nc,)
+        shape_b = (nf - nif, ncomp) if ncomp > 1 else (nf - nif,)
+        i = np.zeros(shape_i)
+        b = np.zeros(shape_b)
+        bc = np.zeros(npch, dtype=np.int32)
+        dp = C.POINTER(C.c_double)
+        if lib.smg_read_field(self.h, path.encode(), ncomp, i.ctypes.data_as(dp), b.ctypes.data_as(dp),
+                              bc.ctypes.data_as(C.POINTER(C.c_int32))):
+            raise FoamIOError(lib.smg_io_error().decode())
+        return i, b, bc
+
+
+def hex_block_handle(*args, **kw) -> MeshHandle:
+    return MeshHandle(hex_block(*args, _keep=True, **kw))
+
+
+def read_polymesh(polymesh_dir: str) -> MeshHandle:
+    """constant/polyMesh of a serial case or of one processorN directory (ascii or binary)."""
+    return MeshHandle(_meshgen().smg_read_polymesh(polymesh_dir.encode()))
+
+
+def read_decomposed_case(case_dir: str, n_procs: int):
+    """processor0..N-1/constant/polyMesh, with the processor-patch weights / deltaCoeffs completed from the
+    neighbour side (what processorFvPatch::makeWeights gets through its geometry exchange)."""
+    hs = [read_polymesh(os.path.join(case_dir, f"processor{r}", "constant", "polyMesh")) for r in range(n_procs)]
+    arr = (C.c_void_p * n_procs)(*[h.h for h in hs])
+    if _meshgen().smg_couple_processor_patches(arr, n_procs):
+        raise FoamIOError(_meshgen().smg_io_error().decode())
+    return hs

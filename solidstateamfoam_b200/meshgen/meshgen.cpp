@@ -20,8 +20,15 @@
 // and mapped by an affine matrix A (sheared hex => non-orthogonal mesh), so the exact
 // centroids/areas/volumes are available in closed form.
 
+#include <sys/stat.h>
+
 #include <algorithm>
+#include <cctype>
 #include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -45,6 +52,10 @@ struct Mesh {
     std::vector<int32_t> cellGlobal;  // local cell -> global cell
     std::vector<int32_t> faceGlobal;  // local face -> global face (sign in flip)
     std::vector<int32_t> faceFlip;    // 1 if the local face is the flipped global face
+    // optional point/face topology (hex blocks; polyMesh reader): what constant/polyMesh/{points,faces} hold
+    std::vector<double> points;          // 3*nPoints
+    std::vector<int32_t> faceVertStart;  // nFaces+1
+    std::vector<int32_t> faceVerts;
 };
 
 struct Vec3 {
@@ -157,6 +168,30 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
     const double detA = A.det();
 
     auto cid = [&](int i, int j, int k) { return int32_t(i + int64_t(nx) * (j + int64_t(ny) * k)); };
+    // points and face vertex lists (right-hand rule: the face normal points owner -> neighbour / outward)
+    auto pid = [&](int i, int j, int k) { return int32_t(i + int64_t(nx + 1) * (j + int64_t(ny + 1) * k)); };
+    m.points.resize(3 * size_t(nx + 1) * (ny + 1) * (nz + 1));
+    for (int k = 0; k <= nz; ++k)
+        for (int j = 0; j <= ny; ++j)
+            for (int i = 0; i <= nx; ++i) put3(m.points, pid(i, j, k), A.apply({xs[i], ys[j], zs[k]}));
+    m.faceVertStart.assign(1, 0);
+    m.faceVerts.reserve(4 * size_t(m.nFaces));
+    // quad normal to `axis` at grid index (i,j,k) of its low corner; positive = normal along +axis
+    auto quad = [&](int axis, int i, int j, int k, bool positive) {
+        int32_t v[4];
+        if (axis == 0) {
+            v[0] = pid(i, j, k); v[1] = pid(i, j + 1, k); v[2] = pid(i, j + 1, k + 1); v[3] = pid(i, j, k + 1);
+        } else if (axis == 1) {
+            v[0] = pid(i, j, k); v[1] = pid(i, j, k + 1); v[2] = pid(i + 1, j, k + 1); v[3] = pid(i + 1, j, k);
+        } else {
+            v[0] = pid(i, j, k); v[1] = pid(i + 1, j, k); v[2] = pid(i + 1, j + 1, k); v[3] = pid(i, j + 1, k);
+        }
+        if (positive)
+            for (int q = 0; q < 4; ++q) m.faceVerts.push_back(v[q]);
+        else
+            for (int q = 0; q < 4; ++q) m.faceVerts.push_back(v[(4 - q) % 4]);
+        m.faceVertStart.push_back(int32_t(m.faceVerts.size()));
+    };
 
     int64_t f = 0;
     for (int k = 0; k < nz; ++k)
@@ -173,6 +208,7 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                     m.neighbour[f] = cid(i + 1, j, k);
                     put3(m.Sf, f, mappedArea(A, 0, dy, dz));
                     put3(m.Cf, f, A.apply({xs[i + 1], cy, cz}));
+                    quad(0, i + 1, j, k, true);
                     ++f;
                 }
                 if (j + 1 < ny) {
@@ -180,6 +216,7 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                     m.neighbour[f] = cid(i, j + 1, k);
                     put3(m.Sf, f, mappedArea(A, 1, dz, dx));
                     put3(m.Cf, f, A.apply({cx, ys[j + 1], cz}));
+                    quad(1, i, j + 1, k, true);
                     ++f;
                 }
                 if (k + 1 < nz) {
@@ -187,6 +224,7 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                     m.neighbour[f] = cid(i, j, k + 1);
                     put3(m.Sf, f, mappedArea(A, 2, dx, dy));
                     put3(m.Cf, f, A.apply({cx, cy, zs[k + 1]}));
+                    quad(2, i, j, k + 1, true);
                     ++f;
                 }
             }
@@ -230,6 +268,7 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                     put3(m.Sf, f, {sgn * S.x, sgn * S.y, sgn * S.z});
                     put3(m.Cf, f,
                          A.apply({hi ? xs[nx] : xs[0], 0.5 * (ys[j] + ys[j + 1]), 0.5 * (zs[k] + zs[k + 1])}));
+                    quad(0, hi ? nx : 0, j, k, hi);
                     ++f;
                 }
         } else if (axis == 1) {
@@ -242,6 +281,7 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                     put3(m.Sf, f, {sgn * S.x, sgn * S.y, sgn * S.z});
                     put3(m.Cf, f,
                          A.apply({0.5 * (xs[i] + xs[i + 1]), hi ? ys[ny] : ys[0], 0.5 * (zs[k] + zs[k + 1])}));
+                    quad(1, i, hi ? ny : 0, k, hi);
                     ++f;
                 }
         } else {
@@ -254,6 +294,7 @@ Mesh* hexBlock(int nx, int ny, int nz, const double* origin, const double* len, 
                     put3(m.Sf, f, {sgn * S.x, sgn * S.y, sgn * S.z});
                     put3(m.Cf, f,
                          A.apply({0.5 * (xs[i] + xs[i + 1]), 0.5 * (ys[j] + ys[j + 1]), hi ? zs[nz] : zs[0]}));
+                    quad(2, i, j, hi ? nz : 0, hi);
                     ++f;
                 }
         }
@@ -576,6 +617,8 @@ void decompose(const Mesh& g, const int32_t* cellProc, int nProcs, Mesh** out) {
     }
 }
 
+#include "foam_io.inc"
+
 }  // namespace
 
 extern "C" {
@@ -627,6 +670,60 @@ SMG_GETTER(C, double, C)
 SMG_GETTER(cell_global, int32_t, cellGlobal)
 SMG_GETTER(face_global, int32_t, faceGlobal)
 SMG_GETTER(face_flip, int32_t, faceFlip)
+
+SMG_GETTER(points, double, points)
+SMG_GETTER(face_vert_start, int32_t, faceVertStart)
+SMG_GETTER(face_verts, int32_t, faceVerts)
+int64_t smg_n_points(const smg_mesh* mm) { return int64_t(reinterpret_cast<const Mesh*>(mm)->points.size() / 3); }
+
+// ---- OpenFOAM case I/O (foam_io.inc) ----
+int smg_write_polymesh(const smg_mesh* mm, const char* polyMeshDir, int binary) {
+    try {
+        writePolyMesh(*reinterpret_cast<const Mesh*>(mm), polyMeshDir, binary != 0);
+        return 0;
+    } catch (const std::exception& e) {
+        g_ioError = e.what();
+        return 1;
+    }
+}
+smg_mesh* smg_read_polymesh(const char* polyMeshDir) {
+    try {
+        return reinterpret_cast<smg_mesh*>(readPolyMesh(polyMeshDir));
+    } catch (const std::exception& e) {
+        g_ioError = e.what();
+        return nullptr;
+    }
+}
+int smg_couple_processor_patches(smg_mesh** meshes, int n) {
+    try {
+        coupleProcessorPatches(reinterpret_cast<Mesh**>(meshes), n);
+        return 0;
+    } catch (const std::exception& e) {
+        g_ioError = e.what();
+        return 1;
+    }
+}
+int smg_write_field(const smg_mesh* mm, const char* path, const char* name, int ncomp, const double* internal,
+                    const double* boundary, const int32_t* patchBc, int binary) {
+    try {
+        writeVolField(*reinterpret_cast<const Mesh*>(mm), path, name, ncomp, internal, boundary, patchBc, binary != 0);
+        return 0;
+    } catch (const std::exception& e) {
+        g_ioError = e.what();
+        return 1;
+    }
+}
+int smg_read_field(const smg_mesh* mm, const char* path, int ncomp, double* internal, double* boundary,
+                   int32_t* patchBc) {
+    try {
+        readVolField(*reinterpret_cast<const Mesh*>(mm), path, ncomp, internal, boundary, patchBc);
+        return 0;
+    } catch (const std::exception& e) {
+        g_ioError = e.what();
+        return 1;
+    }
+}
+const char* smg_io_error() { return g_ioError.c_str(); }
 
 const char* smg_patch_name(const smg_mesh* mm, int p) {
     return reinterpret_cast<const Mesh*>(mm)->patchName[p].c_str();

@@ -115,3 +115,29 @@ def test_driver_reference_error_behaviour(tmp_path):
     open(tp, "w").write(ttxt.replace("        A ", "        Amissing "))
     r = subprocess.run([DRIVER, d, "1", str(tmp_path / "o.bin")], capture_output=True, text=True)
     assert r.returncode == 1 and "keyword A is undefined in dictionary" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("binary", [False, True])
+def test_driver_on_openfoam_case_directory(tmp_path, binary):
+    """a real OpenFOAM case layout (polyMesh + 0/ fields + dictionaries) in, OpenFOAM fields out"""
+    from solidstateamfoam_b200 import mesh as M
+
+    shear = (1.0, 0.3, 0.1, 0.0, 1.0, 0.2, 0.0, 0.0, 1.0)
+    case = cases.cfg1(dims=(10, 8, 6), affine=shear)
+    h = M.hex_block_handle(10, 8, 6, length=case.mesh.meta["length"], affine=shear)
+    d = str(tmp_path / "foamCase")
+    cases.write_foam_case(d, case, h, binary=binary)
+    _build.build_host()
+    r = subprocess.run([DRIVER, d, "2", str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # the oracle runs on the mesh as the driver saw it: geometry recomputed from points and faces
+    rd = M.read_polymesh(os.path.join(d, "constant", "polyMesh"))
+    import copy
+    ing = copy.copy(case)
+    ing.mesh = rd.mesh()
+    oc = oracle_sequence(ing)
+    for name, f in (("epsilonDotEq", P.F_EPSDOT), ("nu", P.F_NU), ("muEff", P.F_MUEFF), ("k", P.F_K),
+                    ("qvisc", P.F_QVISC), ("qfric", P.F_QFRIC), ("sigmay", P.F_SIGMAY)):
+        gi, gb, _ = rd.read_field(os.path.join(d, "2", name), 1)
+        check_field(name, np.concatenate([gi, gb]), oc.field(f), f in BIT_EXACT)
