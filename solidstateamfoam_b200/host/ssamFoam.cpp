@@ -25,7 +25,15 @@ std::string sortedToc(const std::vector<word>& keys) {
 // ---- dictionary parser ----------------------------------------------------------------------------------------
 class dictParser {
 public:
-    explicit dictParser(const std::string& text) { tokenize(text); }
+    explicit dictParser(const std::string& text) {
+        // "format binary;" in the FoamFile header: nonuniform List<T> payloads are raw bytes, skipped here
+        const size_t h = text.find("FoamFile");
+        if (h != std::string::npos) {
+            const size_t e = text.find('}', h);
+            binary_ = e != std::string::npos && text.substr(h, e - h).find("binary") != std::string::npos;
+        }
+        tokenize(text);
+    }
     void parseInto(dictionary& d, bool top) {
         while (pos_ < tok_.size()) {
             const std::string t = tok_[pos_];
@@ -68,6 +76,14 @@ private:
             } else if (c == '{' || c == '}' || c == '(' || c == ')' || c == ';') {
                 tok_.push_back(std::string(1, c));
                 ++i;
+                if (binary_ && c == '(' && tok_.size() >= 3) {
+                    // ... List<vector> N ( <N*ncomp*8 raw bytes> )
+                    const std::string& type = tok_[tok_.size() - 3];
+                    int nc = type == "List<scalar>" ? 1 : type == "List<vector>" ? 3 : type == "List<tensor>" ? 9 : 0;
+                    char* end = nullptr;
+                    const long n = std::strtol(tok_[tok_.size() - 2].c_str(), &end, 10);
+                    if (nc && *end == '\0' && n >= 0) i += size_t(n) * nc * 8;
+                }
             } else {
                 size_t j = i;
                 while (j < s.size() && !std::isspace((unsigned char)s[j]) && std::string("{}();").find(s[j]) == std::string::npos)
@@ -79,6 +95,7 @@ private:
     }
     std::vector<std::string> tok_;
     size_t pos_ = 0;
+    bool binary_ = false;
 };
 
 dictionary dictionary::fromString(const std::string& text, const std::string& name) {
