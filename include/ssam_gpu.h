@@ -101,7 +101,14 @@ enum {
     SSAM_F_STRAINRATE = 17, /* viscosityModel::strainRate() = sqrt(2)|symm(grad U)| (NortonHoff.C:62) */
     SSAM_F_RHO_SOLVER = 18, /* rho   == alpha1*rho1 + alpha2*rho2        (alphaEqnSubCycle.H:41)    */
     SSAM_F_RHOCP = 19,      /* rhoCp == alpha1*rho1*cp1 + alpha2*rho2*cp2 (alphaEqnSubCycle.H:42)   */
-    SSAM_F_COUNT = 20
+    /* fluid/calculateStrain.H post-processing */
+    SSAM_F_PRGH = 20,       /* p_rgh, in                                                            */
+    SSAM_F_Z = 21,          /* Z = epsilonDotEq*exp(Q/(R*temp))                 (calculateStrain.H:12) */
+    SSAM_F_SIGMAF_PP = 22,  /* the solver's own "sigmaf" (createStressStrain.H:36, calculateStrain.H:13) */
+    SSAM_F_DEPSEQ = 23,     /* dEpsilonEq = sqrt(4/3*J2)                        (calculateStrain.H:35) */
+    SSAM_F_EPSEQ = 24,      /* epsilonEq, in/out: += dEpsilonEq                 (calculateStrain.H:40) */
+    SSAM_F_SIGMAVM = 25,    /* von Mises stress                                 (calculateStrain.H:92) */
+    SSAM_F_COUNT = 26
 };
 
 /* ---- model parameters (what the reference reads from dictionaries) ---------- */
@@ -158,6 +165,12 @@ typedef struct ssam_rotslip_params {
     double delta;              /* constantRotationalSlip   */
     double omega0, delta0, R0; /* exponentialRotationalSlip */
 } ssam_rotslip_params;
+
+/* fluid/calculateStrain.H: constants looked up in the phase-1 dictionary (:6-10) + runTime.deltaT() */
+typedef struct ssam_stress_strain_params {
+    double Q, R, sigmaR, A, n;
+    double deltaT;
+} ssam_stress_strain_params;
 
 /* everything one fused update needs (benchmark path) */
 typedef struct ssam_update_params {
@@ -253,6 +266,11 @@ SSAM_API ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_par
 SSAM_API ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p);
 /* patch centroid of the friction patch after the cross-rank sum (constantSlipStick.C:118-138) */
 SSAM_API ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* area);
+
+/* fluid/calculateStrain.H:1-35,77-94 (the explicit part; the epsilonEq transport solve :45-58 stays in
+ * OpenFOAM): another fvc::grad(U) -> GRADU, then Z, SIGMAF_PP, DEPSEQ, EPSEQ += DEPSEQ, SIGMAVM.
+ * Reads U, EPSDOT, T, MUEFF, PRGH, EPSEQ. */
+SSAM_API ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p);
 
 /* ---- fused entry point (the benchmarked path) ---------------------------------------------------
  * One pass: grad(U) -> EPSDOT -> nuModel1/2.correct() (NU1,SIGMAF,SIGMAY,NU2) -> NU -> MUEFF ->

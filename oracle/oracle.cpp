@@ -787,6 +787,119 @@ int strainRate(Case& c, double factor, int outField, int form) {
     return 0;
 }
 
+// ================================================================================================
+// fluid/calculateStrain.H:1-35,77-94 (the explicit stress / strain post-processing)
+// ================================================================================================
+// OpenFOAM tensor semantics restated: T() transpose, tr = xx+yy+zz, Tensor - SphericalTensor touches the
+// diagonal only, A && B = sum_ij A_ij*B_ij in row-major order, dev(T) = T - (1/3)*tr(T)*I.
+inline void stressStrainPoint(const ssam_stress_strain_params& p, const double* g, double eps, double T, double mu,
+                              double prgh, double& Z, double& sf, double& dEq, double& svm) {
+    Z = eps * std::exp(p.Q / (p.R * T));                                  // :12
+    sf = p.sigmaR * std::asinh(libmPow(Z / p.A, 1 / p.n));                // :13
+    double dE[9], eD[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const double sym = 0.5 * (g[3 * i + j] + g[3 * j + i]);       // 0.5*(gradU + gradU.T())
+            dE[3 * i + j] = sym * p.deltaT;                               // :18
+            eD[3 * i + j] = sym;                                          // :79
+        }
+    const double third = 1.0 / 3.0;
+    // :22  dDevEpsilon = dEpsilon - 1.0/3.0*tr(dEpsilon)*I
+    const double s1 = third * (dE[0] + dE[4] + dE[8]);
+    double dD[9];
+    for (int k = 0; k < 9; ++k) dD[k] = dE[k];
+    dD[0] = dE[0] - s1; dD[4] = dE[4] - s1; dD[8] = dE[8] - s1;
+    // :26  J2s = 0.5*(pow(tr(dDevEpsilon),2) - (dDevEpsilon && dDevEpsilon))
+    double dd = dD[0] * dD[0];
+    for (int k = 1; k < 9; ++k) dd += dD[k] * dD[k];
+    const double J2s = 0.5 * (libmPow(dD[0] + dD[4] + dD[8], 2) - dd);
+    const double J2 = std::sqrt(libmPow(J2s, 2));                         // :29
+    dEq = std::sqrt((4.0 / 3.0) * J2);                                    // :35
+    // :82-92  dev(epsilonDot), shear stress, total stress, its deviator, von Mises
+    const double s2 = third * (eD[0] + eD[4] + eD[8]);
+    double sh[9];
+    for (int k = 0; k < 9; ++k) sh[k] = eD[k];
+    sh[0] = eD[0] - s2; sh[4] = eD[4] - s2; sh[8] = eD[8] - s2;
+    const double twoMu = 2.0 * mu;
+    for (int k = 0; k < 9; ++k) sh[k] = twoMu * sh[k];                    // :85
+    double st[9];
+    for (int k = 0; k < 9; ++k) st[k] = sh[k];
+    st[0] = prgh + sh[0]; st[4] = prgh + sh[4]; st[8] = prgh + sh[8];     // :88  p_rgh*I + shearStress
+    const double s3 = third * (st[0] + st[4] + st[8]);
+    st[0] -= s3; st[4] -= s3; st[8] -= s3;                                // :91
+    double ss = st[0] * st[0];
+    for (int k = 1; k < 9; ++k) ss += st[k] * st[k];
+    svm = std::sqrt(2.3 / 3.0) * std::sqrt(ss);                           // :94  (2.3/3.0 as written)
+}
+
+int stressStrain(Case& c, const ssam_stress_strain_params& p, int form) {
+    const int needF[] = {SSAM_F_U, SSAM_F_EPSDOT, SSAM_F_T, SSAM_F_MUEFF, SSAM_F_PRGH};
+    for (int f : needF)
+        if (!c.set[f]) {
+            c.err = "calculateStrain: U / epsilonDotEq / temp / muEff / p_rgh not available";
+            return SSAM_ERR_MISSING_FIELD;
+        }
+    Fld& G = fieldRef(c, SSAM_F_GRADU);
+    if (form == 0)
+        gradFaithful(c, c.f[SSAM_F_U], G);
+    else
+        gradFused(c, c.f[SSAM_F_U], G);
+    c.set[SSAM_F_GRADU] = true;
+    const size_t n = c.nTot;
+    const Fld &eps = c.f[SSAM_F_EPSDOT], &T = c.f[SSAM_F_T], &mu = c.f[SSAM_F_MUEFF], &pr = c.f[SSAM_F_PRGH];
+    Fld &Z = fieldRef(c, SSAM_F_Z), &sf = fieldRef(c, SSAM_F_SIGMAF_PP), &dEq = fieldRef(c, SSAM_F_DEPSEQ),
+        &eEq = fieldRef(c, SSAM_F_EPSEQ), &svm = fieldRef(c, SSAM_F_SIGMAVM);
+    if (form == 1) {
+        for (size_t i = 0; i < n; ++i) stressStrainPoint(p, &G[9 * i], eps[i], T[i], mu[i], pr[i], Z[i], sf[i], dEq[i], svm[i]);
+    } else {
+        // field-at-a-time with tensor temporaries, one pass per operator as calculateStrain.H writes them
+        Z = mulFF(eps, expF(divSF(p.Q, mulSF(p.R, T))));
+        sf = mulSF(p.sigmaR, asinhF(powFS(divFS(Z, p.A), 1 / p.n)));
+        auto tens = [&]() { return Fld(9 * n); };
+        Fld GT = tens(), sum = tens(), sym = tens(), dE = tens();
+        for (size_t i = 0; i < n; ++i)
+            for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) GT[9 * i + 3 * a + b] = G[9 * i + 3 * b + a];
+        LOOP(9 * n) sum[i] = G[i] + GT[i];
+        LOOP(9 * n) sym[i] = 0.5 * sum[i];
+        LOOP(9 * n) dE[i] = sym[i] * p.deltaT;
+        auto trF = [&](const Fld& t) { Fld r(n); LOOP(n) r[i] = t[9 * i] + t[9 * i + 4] + t[9 * i + 8]; return r; };
+        auto minusSph = [&](const Fld& t, const Fld& sph) {
+            Fld r = t;
+            LOOP(n) { r[9 * i] = t[9 * i] - sph[i]; r[9 * i + 4] = t[9 * i + 4] - sph[i]; r[9 * i + 8] = t[9 * i + 8] - sph[i]; }
+            return r;
+        };
+        auto ddot = [&](const Fld& a, const Fld& b) {
+            Fld r(n);
+            LOOP(n) { double s = a[9 * i] * b[9 * i]; for (int k = 1; k < 9; ++k) s += a[9 * i + k] * b[9 * i + k]; r[i] = s; }
+            return r;
+        };
+        Fld dD = minusSph(dE, mulSF(1.0 / 3.0, trF(dE)));
+        Fld dd = ddot(dD, dD);
+        Fld t2 = powFS(trF(dD), 2);
+        Fld diff(n);
+        LOOP(n) diff[i] = t2[i] - dd[i];
+        Fld J2s = mulSF(0.5, diff);
+        Fld J2p = powFS(J2s, 2), J2(n);
+        LOOP(n) J2[i] = std::sqrt(J2p[i]);
+        Fld a43 = mulSF(4.0 / 3.0, J2);
+        LOOP(n) dEq[i] = std::sqrt(a43[i]);
+        Fld eDev = minusSph(sym, mulSF(1.0 / 3.0, trF(sym)));
+        Fld twoMu = mulSF(2.0, mu), sh = tens();
+        LOOP(n) for (int k = 0; k < 9; ++k) sh[9 * i + k] = twoMu[i] * eDev[9 * i + k];
+        Fld st = sh;
+        LOOP(n) { st[9 * i] = pr[i] + sh[9 * i]; st[9 * i + 4] = pr[i] + sh[9 * i + 4]; st[9 * i + 8] = pr[i] + sh[9 * i + 8]; }
+        Fld sdev = minusSph(st, mulSF(1.0 / 3.0, trF(st)));
+        Fld ss = ddot(sdev, sdev), rt(n);
+        LOOP(n) rt[i] = std::sqrt(ss[i]);
+        svm = mulSF(std::sqrt(2.3 / 3.0), rt);
+    }
+    if (!c.set[SSAM_F_EPSEQ]) std::fill(eEq.begin(), eEq.end(), 0.0);  // createStressStrain.H: initial value zero
+    for (size_t i = 0; i < n; ++i) eEq[i] += dEq[i];                     // :40  epsilonEq += dEpsilonEq
+    for (int f : {SSAM_F_Z, SSAM_F_SIGMAF_PP, SSAM_F_DEPSEQ, SSAM_F_EPSEQ, SSAM_F_SIGMAVM}) c.set[f] = true;
+    return 0;
+}
+
 // the fused update = the staged calls in the order documented in include/ssam_gpu.h
 int update(Case& c, const ssam_update_params& p, const double* sums, int form) {
     int e;
@@ -884,6 +997,7 @@ int orc_mixture_cp(orc_case* h, const ssam_mixture_params* p, int form) {
 }
 int orc_mixture_k(orc_case* h, const ssam_mixture_params* p, int form) { return mixtureK(CASE(h), *p, form); }
 int orc_solver_rho_rhocp(orc_case* h, const ssam_mixture_params* p, int form) { return solverRhoRhoCp(CASE(h), *p, form); }
+int orc_stress_strain(orc_case* h, const ssam_stress_strain_params* p, int form) { return stressStrain(CASE(h), *p, form); }
 void orc_friction_patch_sums(orc_case* h, int patch, double* out4) { patchSums(CASE(h), patch, out4); }
 int orc_friction_correct(orc_case* h, const ssam_stick_params* p, const double* sums, int form) {
     Case& c = CASE(h);

@@ -45,6 +45,7 @@ def lib():
         for n in ("calc_nu", "mu", "rho", "cp", "k"):
             getattr(L, "orc_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
+        L.orc_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams), C.c_int]
         L.orc_friction_patch_sums.argtypes = [vp, C.c_int, dp]
         L.orc_friction_correct.argtypes = [vp, C.POINTER(P.StickParams), dp, C.c_int]
         L.orc_friction_patch_centre.argtypes = [vp, dp, dp]
@@ -133,6 +134,9 @@ class OracleCase:
 
     def solver_rho_rhocp(self, p, form=FAITHFUL):
         self._chk(lib().orc_solver_rho_rhocp(self.h, C.byref(p), form))
+
+    def stress_strain(self, p, form=FAITHFUL):
+        self._chk(lib().orc_stress_strain(self.h, C.byref(p), form))
 
     def friction_patch_sums(self, patch):
         out = np.zeros(4)

@@ -22,7 +22,7 @@ SYMBOLS = [
     "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
-    "ssam_solver_rho_rhocp", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
+    "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
 ]
 
@@ -79,6 +79,7 @@ def load():
     for n in ("calc_nu", "mu", "rho", "cp", "k"):
         getattr(L, "ssam_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams)]
+    L.ssam_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams)]
     L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
@@ -234,6 +235,9 @@ class Context:
 
     def solver_rho_rhocp(self, p: P.MixtureParams):
         self._chk(self.L.ssam_solver_rho_rhocp(self.h, C.byref(p)))
+
+    def stress_strain(self, p: P.StressStrainParams):
+        self._chk(self.L.ssam_stress_strain(self.h, C.byref(p)))
 
     def friction_correct(self, p: P.StickParams):
         self._chk(self.L.ssam_friction_correct(self.h, C.byref(p)))

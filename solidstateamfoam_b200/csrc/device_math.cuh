@@ -130,6 +130,52 @@ SSAM_DEV double phaseK(const ssam_conductivity& k, double shift, double T) {
     return k.k * selfRatio(T);  // :269
 }
 
+// ---- fluid/calculateStrain.H:1-35,77-94: explicit stress / strain post-processing --------------------
+// OpenFOAM tensor semantics: T() transpose, tr = xx+yy+zz, Tensor - SphericalTensor touches the diagonal
+// only, A && B = sum_ij A_ij*B_ij in row-major order.  pow(x,2) as a product (<= 1 ulp from libm's pow).
+struct StressStrainOut {
+    double Z, sigmaf, dEpsilonEq, sigmavm;
+};
+SSAM_DEV StressStrainOut stressStrain(const ssam_stress_strain_params& p, double logA, double invN,
+                                      const double (&g)[9], double eps, double T, double mu, double prgh) {
+    StressStrainOut o;
+    const double q = divFast(p.Q, p.R * T);
+    o.Z = eps * fastExp(q);                                               // :12
+    o.sigmaf = p.sigmaR * swAsinhOfLog((fastLog(eps) + (q - logA)) * invN);  // :13 in the log domain
+    double dE[9], eD[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double sym = 0.5 * (g[3 * i + j] + g[3 * j + i]);
+            dE[3 * i + j] = sym * p.deltaT;                               // :18
+            eD[3 * i + j] = sym;                                          // :79
+        }
+    const double third = 1.0 / 3.0;
+    const double s1 = third * (dE[0] + dE[4] + dE[8]);                    // :22
+    dE[0] = dE[0] - s1; dE[4] = dE[4] - s1; dE[8] = dE[8] - s1;
+    double dd = dE[0] * dE[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) dd += dE[k] * dE[k];
+    const double trD = dE[0] + dE[4] + dE[8];
+    const double J2s = 0.5 * (trD * trD - dd);                            // :26
+    const double J2 = sqrt(J2s * J2s);                                    // :29
+    o.dEpsilonEq = sqrt((4.0 / 3.0) * J2);                                // :35
+    const double s2 = third * (eD[0] + eD[4] + eD[8]);                    // dev(epsilonDot) :82
+    eD[0] = eD[0] - s2; eD[4] = eD[4] - s2; eD[8] = eD[8] - s2;
+    const double twoMu = 2.0 * mu;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) eD[k] = twoMu * eD[k];                    // shearStress :85
+    eD[0] = prgh + eD[0]; eD[4] = prgh + eD[4]; eD[8] = prgh + eD[8];     // sigmaTot :88
+    const double s3 = third * (eD[0] + eD[4] + eD[8]);
+    eD[0] -= s3; eD[4] -= s3; eD[8] -= s3;                                // sigmadev :91
+    double ss = eD[0] * eD[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) ss += eD[k] * eD[k];
+    o.sigmavm = sqrt(2.3 / 3.0) * sqrt(ss);                               // :94
+    return o;
+}
+
 // ---- friction (constantSlipStick.C / exponentialSlipStick.C) ---------------------------------------
 SSAM_DEV double qviscOf(double betaTQ, double mu, double e) { return ((3.0 * betaTQ) * mu) * (e * e); }  // :58
 

@@ -1118,6 +1118,36 @@ ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p) {
     return finish(ctx);
 }
 
+ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(need(ctx, SSAM_F_EPSDOT, "epsilonDotEq"));
+    TRY(need(ctx, SSAM_F_T, "temp"));
+    TRY(need(ctx, SSAM_F_MUEFF, "muEff"));
+    TRY(need(ctx, SSAM_F_PRGH, "p_rgh"));
+    TRY(gradOrStrain(ctx, false, 0.0, SSAM_F_GRADU));  // volTensorField gradU = fvc::grad(U)  (:17)
+    const int outs[] = {SSAM_F_Z, SSAM_F_SIGMAF_PP, SSAM_F_DEPSEQ, SSAM_F_EPSEQ, SSAM_F_SIGMAVM};
+    const bool accumulate = ctx->isSet[SSAM_F_EPSEQ];
+    for (int f : outs) TRY(ensureField(ctx, f));
+    StressStrainStage s;
+    s.p = *p;
+    s.logA = std::log(p->A);
+    s.invN = 1 / p->n;
+    for (int k = 0; k < 9; ++k) s.g[k] = ctx->plane[SSAM_F_GRADU][k];
+    s.eps = ctx->plane[SSAM_F_EPSDOT][0];
+    s.T = ctx->plane[SSAM_F_T][0];
+    s.mu = ctx->plane[SSAM_F_MUEFF][0];
+    s.prgh = ctx->plane[SSAM_F_PRGH][0];
+    s.Z = ctx->plane[SSAM_F_Z][0];
+    s.sigmaf = ctx->plane[SSAM_F_SIGMAF_PP][0];
+    s.dEq = ctx->plane[SSAM_F_DEPSEQ][0];
+    s.epsEq = ctx->plane[SSAM_F_EPSEQ][0];
+    s.sigmavm = ctx->plane[SSAM_F_SIGMAVM][0];
+    s.accumulate = accumulate ? 1 : 0;
+    LAUNCH((k_map<StressStrainStage>), mapGrid(ctx), 256, ctx->nTot, s);
+    for (int f : outs) ctx->isSet[f] = true;
+    return finish(ctx);
+}
+
 ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p) {
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     CHECK(p->model == SSAM_STICK_CONSTANT || p->model == SSAM_STICK_EXPONENTIAL, SSAM_ERR_UNKNOWN_MODEL,

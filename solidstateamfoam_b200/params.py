@@ -11,9 +11,11 @@ BC_VALUE, BC_ZERO_GRADIENT = 0, 1
 
 (F_U, F_T, F_ALPHA1, F_P, F_EPSDOT, F_NU1, F_NU2, F_SIGMAF, F_SIGMAY, F_NU, F_MUEFF, F_RHO, F_CP, F_K, F_QVISC,
  F_QFRIC, F_GRADU, F_STRAINRATE, F_RHO_SOLVER, F_RHOCP) = range(20)
-F_COUNT = 20
+F_PRGH, F_Z, F_SIGMAF_PP, F_DEPSEQ, F_EPSEQ, F_SIGMAVM = range(20, 26)
+F_COUNT = 26
 FIELD_NAMES = ["U", "temp", "alpha1", "p", "epsilonDotEq", "nu1", "nu2", "sigmaf", "sigmay", "nu", "muEff", "rho",
-               "cp", "k", "qvisc", "qfric", "gradU", "strainRate", "rhoSolver", "rhoCp"]
+               "cp", "k", "qvisc", "qfric", "gradU", "strainRate", "rhoSolver", "rhoCp", "p_rgh", "Z", "sigmafPP",
+               "dEpsilonEq", "epsilonEq", "sigmavm"]
 
 
 def ncomp(field: int) -> int:
@@ -75,6 +77,11 @@ class StickParams(C.Structure):
 class RotSlipParams(C.Structure):
     _fields_ = [("model", C.c_int32), ("patch", C.c_int32), ("omega", C.c_double * 3), ("Vt", C.c_double * 3),
                 ("delta", C.c_double), ("omega0", C.c_double), ("delta0", C.c_double), ("R0", C.c_double)]
+
+
+class StressStrainParams(C.Structure):
+    _fields_ = [("Q", C.c_double), ("R", C.c_double), ("sigmaR", C.c_double), ("A", C.c_double), ("n", C.c_double),
+                ("deltaT", C.c_double)]
 
 
 class UpdateParams(C.Structure):

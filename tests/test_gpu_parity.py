@@ -253,3 +253,29 @@ def test_degenerate_meshes(ctx, dims):
         for which in (P.ADDR_OWNER_START, P.ADDR_EXTRA_START, P.ADDR_EXTRA_FACE, P.ADDR_CELL_FACES, P.ADDR_FACE_COLOUR):
             assert ctx.addressing(which).tobytes() == oc.addressing(which).tobytes()
     ctx.set_cell_kernel(1)
+
+
+@pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg3_poly"])
+def test_stress_strain_post_processing(ctx, name):
+    """fluid/calculateStrain.H: Z, sigmaf, dEpsilonEq, epsilonEq += , sigmavm"""
+    case = small_cases()[name]()
+    ctx.load_case(case)
+    ctx.update_fused(case.params, 0)
+    oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
+    n, nb = case.mesh.nCells, case.mesh.nBoundaryFaces
+    prgh = 1e5 * (1.0 + 0.05 * np.random.default_rng(5).standard_normal(n + nb))
+    ctx.upload(P.F_PRGH, prgh[:n], prgh[n:])
+    oc.set(P.F_PRGH, prgh[:n], prgh[n:])
+    # identical inputs on both sides: muEff from the fused update agrees with the oracle's only to ~1e-14,
+    # and sigmavm subtracts p_rgh*I (|p| ~ 1e5 against shear stresses down to 1e-3), which would amplify it
+    ctx.upload(P.F_MUEFF, oc.internal(P.F_MUEFF), oc.boundary(P.F_MUEFF))
+    v = case.params.visc1
+    prm = P.StressStrainParams(Q=v.Q, R=v.R, sigmaR=v.sigmaR, A=v.A, n=v.n, deltaT=1e-3)
+    for _ in range(2):  # the second call accumulates epsilonEq
+        ctx.stress_strain(prm)
+        oc.stress_strain(prm)
+    for f in (P.F_Z, P.F_SIGMAF_PP, P.F_DEPSEQ, P.F_EPSEQ, P.F_GRADU):
+        gi, gb = ctx.download(f)
+        check_field(P.FIELD_NAMES[f], np.concatenate([gi, gb]), oc.field(f), f in (P.F_GRADU, P.F_DEPSEQ, P.F_EPSEQ))
+    gi, gb = ctx.download(P.F_SIGMAVM)
+    assert np.array_equal(np.concatenate([gi, gb]), oc.field(P.F_SIGMAVM))  # pure IEEE arithmetic

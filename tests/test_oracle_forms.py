@@ -126,3 +126,45 @@ def test_norton_hoff_has_no_sigmay():
     with pytest.raises(O.OracleError) as e:
         oc.friction_correct(stick)
     assert e.value.status == P.ERR_MISSING_FIELD
+
+
+def stress_strain_inputs(case, oc):
+    n, nb = case.mesh.nCells, case.mesh.nBoundaryFaces
+    rng = np.random.default_rng(5)
+    prgh = 1e5 * (1.0 + 0.05 * rng.standard_normal(n + nb))
+    oc.set(P.F_PRGH, prgh[:n], prgh[n:])
+    v = case.params.visc1
+    return P.StressStrainParams(Q=v.Q, R=v.R, sigmaR=v.sigmaR, A=v.A, n=v.n, deltaT=1e-3), prgh
+
+
+def test_stress_strain_forms_agree_and_match_numpy():
+    """fluid/calculateStrain.H: field-at-a-time == per-cell bitwise; values against a numpy evaluation"""
+    case = CASES["cfg1_sheared_graded"]()
+    res = []
+    for form in (O.FAITHFUL, O.FUSED):
+        oc = oracle_update(case, form)
+        prm, prgh = stress_strain_inputs(case, oc)
+        oc.stress_strain(prm, form)
+        oc.stress_strain(prm, form)  # second step accumulates epsilonEq
+        res.append(oc)
+    for f in (P.F_Z, P.F_SIGMAF_PP, P.F_DEPSEQ, P.F_EPSEQ, P.F_SIGMAVM, P.F_GRADU):
+        assert np.array_equal(res[0].field(f), res[1].field(f)), P.FIELD_NAMES[f]
+    oc = res[0]
+    assert np.array_equal(oc.field(P.F_EPSEQ), 2.0 * oc.field(P.F_DEPSEQ))
+    G = oc.field(P.F_GRADU).reshape(-1, 3, 3)
+    dt = 1e-3
+    sym = 0.5 * (G + G.transpose(0, 2, 1))
+    dE = sym * dt
+    I3 = np.eye(3)[None]
+    dD = dE - np.trace(dE, axis1=1, axis2=2)[:, None, None] / 3.0 * I3
+    J2s = 0.5 * (np.trace(dD, axis1=1, axis2=2) ** 2 - np.einsum("nij,nij->n", dD, dD))
+    dEq = np.sqrt(4.0 / 3.0 * np.abs(J2s))
+    assert np.allclose(oc.field(P.F_DEPSEQ), dEq, rtol=1e-10, atol=1e-300)
+    mu, pr = oc.field(P.F_MUEFF), prgh
+    dev = sym - np.trace(sym, axis1=1, axis2=2)[:, None, None] / 3.0 * I3
+    st = pr[:, None, None] * I3 + 2.0 * mu[:, None, None] * dev
+    sd = st - np.trace(st, axis1=1, axis2=2)[:, None, None] / 3.0 * I3
+    svm = np.sqrt(2.3 / 3.0) * np.sqrt(np.einsum("nij,nij->n", sd, sd))
+    assert np.allclose(oc.field(P.F_SIGMAVM), svm, rtol=1e-6, atol=1e-3)  # p*I cancels: conditioning
+    # the solver's own sigmaf equals the SheppardWright model's field (same formula, same inputs)
+    assert np.array_equal(oc.field(P.F_SIGMAF_PP), oc.field(P.F_SIGMAF))
