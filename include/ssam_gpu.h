@@ -108,7 +108,11 @@ enum {
     SSAM_F_DEPSEQ = 23,     /* dEpsilonEq = sqrt(4/3*J2)                        (calculateStrain.H:35) */
     SSAM_F_EPSEQ = 24,      /* epsilonEq, in/out: += dEpsilonEq                 (calculateStrain.H:40) */
     SSAM_F_SIGMAVM = 25,    /* von Mises stress                                 (calculateStrain.H:92) */
-    SSAM_F_COUNT = 26
+    /* interfaceProperties::correct() (called at
+     * immiscibleIncompressibleTwoPhaseThermalMixture.H:80, consumed by alphaEqn.H:154 and UEqn.H:31) */
+    SSAM_F_GRADALPHA = 26,  /* vector, fvc::grad(alpha1, "nHat")                                    */
+    SSAM_F_CURVATURE = 27,  /* interfaceProperties::K_ = -fvc::div(nHatf_)                          */
+    SSAM_F_COUNT = 28
 };
 
 /* ---- model parameters (what the reference reads from dictionaries) ---------- */
@@ -271,6 +275,22 @@ SSAM_API ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3],
  * OpenFOAM): another fvc::grad(U) -> GRADU, then Z, SIGMAF_PP, DEPSEQ, EPSEQ += DEPSEQ, SIGMAVM.
  * Reads U, EPSDOT, T, MUEFF, PRGH, EPSEQ. */
 SSAM_API ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p);
+
+/* interfaceProperties::correct() = calculateK(), the other half of thermo.correct()
+ * (immiscibleIncompressibleTwoPhaseThermalMixture.H:77-81).  The class itself is OpenFOAM v1806 library code
+ * (src/transportModels/interfaceProperties/interfaceProperties.C), restated in oracle/oracle.cpp:
+ *   gradAlpha = fvc::grad(alpha1)  (Gauss linear)      -> GRADALPHA
+ *   nHatfv    = interpolate(gradAlpha)/(mag(interpolate(gradAlpha)) + deltaN);  nHatf = nHatfv & Sf
+ *   K         = -fvc::div(nHatf)                       -> CURVATURE
+ * Reads ALPHA1 (internal + boundary values; flags bit 1 (value 2): refresh processor-patch values first).
+ * No alphaContactAngle patches (the reference's cases have none): correctContactAngle is a no-op.
+ * nHatf_ is a surfaceScalarField (alphaEqn.H:154 `phic*thermo.nHatf()`): nInternalFaces + nBoundaryFaces values. */
+SSAM_API ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags);
+SSAM_API ssam_status ssam_interface_nhatf_download(ssam_ctx* ctx, double* internal_faces, double* boundary_faces);
+SSAM_API double* ssam_interface_nhatf_device_ptr(ssam_ctx* ctx);
+/* deltaN_ = 1e-8/pow(average(mesh.V()), 1.0/3.0) (interfaceProperties constructor); average over all ranks
+ * when a communicator is set. */
+SSAM_API ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN);
 
 /* ---- fused entry point (the benchmarked path) ---------------------------------------------------
  * One pass: grad(U) -> EPSDOT -> nuModel1/2.correct() (NU1,SIGMAF,SIGMAY,NU2) -> NU -> MUEFF ->

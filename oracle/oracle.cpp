@@ -51,9 +51,12 @@ struct Case {
     std::vector<int32_t> ownerStart, extraStart, extraFace, extraOther, cellFacesStart, cellFaces, haloSend,
         haloOffsets, fricCells, faceColour;
     bool addrBuilt = false;
+    Fld nHatf;  // surfaceScalarField: internal faces then boundary faces
 };
 
-int ncompOf(int field) { return field == SSAM_F_U ? 3 : (field == SSAM_F_GRADU ? 9 : 1); }
+int ncompOf(int field) {
+    return (field == SSAM_F_U || field == SSAM_F_GRADALPHA) ? 3 : (field == SSAM_F_GRADU ? 9 : 1);
+}
 
 Fld& fieldRef(Case& c, int field) {
     Fld& v = c.f[field];
@@ -788,6 +791,135 @@ int strainRate(Case& c, double factor, int outField, int form) {
 }
 
 // ================================================================================================
+// interfaceProperties::correct() -> calculateK()   
+// Called by the reference at immiscibleIncompressibleTwoPhaseThermalMixture.H:80; the class is OpenFOAM
+// v1806 library code (src/transportModels/interfaceProperties/interfaceProperties.C), not part of the
+// reference tree, so this is a restatement of its published algorithm:
+//   const volVectorField gradAlpha(fvc::grad(alpha1_, "nHat"));          // Gauss linear
+//   surfaceVectorField gradAlphaf(fvc::interpolate(gradAlpha));          // linear
+//   surfaceVectorField nHatfv(gradAlphaf/(mag(gradAlphaf) + deltaN_));
+//   correctContactAngle(...);                                            // no alphaContactAngle patches: no-op
+//   nHatf_ = nHatfv & Sf;
+//   K_ = -fvc::div(nHatf_);                                              // surfaceIntegrate, then boundary evaluate
+// Stages, so that a multi-rank test can put the processor-patch evaluations in between:
+//   1 cell gradient (+ extrapolated non-coupled boundary values)   [halo GRADALPHA]
+//   2 gaussGrad::correctBoundaryConditions, face normals, nHatf, cell divergence, non-coupled K_b   [halo CURVATURE]
+// ================================================================================================
+int interfaceCorrect(Case& c, double deltaN, int stage) {
+    if (!c.set[SSAM_F_ALPHA1]) {
+        c.err = "alpha1 not set";
+        return SSAM_ERR_MISSING_FIELD;
+    }
+    const Fld& al = c.f[SSAM_F_ALPHA1];
+    Fld& G = fieldRef(c, SSAM_F_GRADALPHA);
+    Fld& K = fieldRef(c, SSAM_F_CURVATURE);
+    const int32_t nC = c.nCells;
+    auto coupled = [&](int p) { return c.patchKind[p] == SSAM_PATCH_PROCESSOR; };
+    if (stage & 1) {
+        // gaussGrad<scalar>::gradf: face values, owner += Sf*ssf, neighbour -= Sf*ssf, boundary +=, /V
+        Fld af(c.nFaces);
+        for (int32_t f = 0; f < c.nIF; ++f) {
+            const double aP = al[c.owner[f]], aN = al[c.neighbour[f]];
+            af[f] = c.w[f] * (aP - aN) + aN;
+        }
+        for (int p = 0; p < c.nPatches; ++p)
+            for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) {
+                const double ab = al[nC + (f - c.nIF)];
+                af[f] = coupled(p) ? c.w[f] * al[c.owner[f]] + (1.0 - c.w[f]) * ab : ab;
+            }
+        std::fill(G.begin(), G.begin() + size_t(nC) * 3, 0.0);
+        for (int32_t f = 0; f < c.nIF; ++f)
+            for (int i = 0; i < 3; ++i) {
+                const double t = c.Sf[3 * size_t(f) + i] * af[f];
+                G[size_t(c.owner[f]) * 3 + i] += t;
+                G[size_t(c.neighbour[f]) * 3 + i] -= t;
+            }
+        for (int32_t f = c.nIF; f < c.nFaces; ++f)
+            for (int i = 0; i < 3; ++i) G[size_t(c.owner[f]) * 3 + i] += c.Sf[3 * size_t(f) + i] * af[f];
+        for (int32_t cc = 0; cc < nC; ++cc)
+            for (int i = 0; i < 3; ++i) G[size_t(cc) * 3 + i] /= c.V[cc];
+        // extrapolatedCalculated: patch value = adjacent cell value (processor patches: neighbour rank's, by halo)
+        for (int p = 0; p < c.nPatches; ++p) {
+            if (coupled(p)) continue;
+            for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f)
+                for (int i = 0; i < 3; ++i) G[size_t(nC + f - c.nIF) * 3 + i] = G[size_t(c.owner[f]) * 3 + i];
+        }
+        c.set[SSAM_F_GRADALPHA] = true;
+    }
+    if (stage & 2) {
+        // gaussGrad::correctBoundaryConditions: g_b += n*(snGrad(alpha)_b - (n & g_b)) on non-coupled patches
+        for (int p = 0; p < c.nPatches; ++p) {
+            if (coupled(p)) continue;
+            for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) {
+                const int32_t b = f - c.nIF, P = c.owner[f];
+                double* gb = &G[size_t(nC + b) * 3];
+                const double ms = c.magSf_b[b];
+                const double n[3] = {c.Sf[3 * size_t(f)] / ms, c.Sf[3 * size_t(f) + 1] / ms, c.Sf[3 * size_t(f) + 2] / ms};
+                const double sn = c.deltaCoeffs_b[b] * (al[nC + b] - al[P]);  // fvPatchField::snGrad()
+                const double ng = n[0] * gb[0] + n[1] * gb[1] + n[2] * gb[2];
+                const double d = sn - ng;
+                for (int i = 0; i < 3; ++i) gb[i] += n[i] * d;
+            }
+        }
+        // fvc::interpolate(gradAlpha), nHatfv, nHatf_
+        c.nHatf.assign(c.nFaces, 0.0);
+        auto normalFlux = [&](const double* gf, int32_t f) {
+            const double m = std::sqrt(gf[0] * gf[0] + gf[1] * gf[1] + gf[2] * gf[2]);
+            const double den = m + deltaN;
+            const double nv[3] = {gf[0] / den, gf[1] / den, gf[2] / den};
+            const double* S = &c.Sf[3 * size_t(f)];
+            return nv[0] * S[0] + nv[1] * S[1] + nv[2] * S[2];
+        };
+        for (int32_t f = 0; f < c.nIF; ++f) {
+            const double* gP = &G[size_t(c.owner[f]) * 3];
+            const double* gN = &G[size_t(c.neighbour[f]) * 3];
+            double gf[3];
+            for (int i = 0; i < 3; ++i) gf[i] = c.w[f] * (gP[i] - gN[i]) + gN[i];
+            c.nHatf[f] = normalFlux(gf, f);
+        }
+        for (int p = 0; p < c.nPatches; ++p)
+            for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) {
+                const double* gb = &G[size_t(nC + f - c.nIF) * 3];
+                double gf[3];
+                if (coupled(p)) {
+                    const double* gP = &G[size_t(c.owner[f]) * 3];
+                    for (int i = 0; i < 3; ++i) gf[i] = c.w[f] * gP[i] + (1.0 - c.w[f]) * gb[i];
+                } else {
+                    for (int i = 0; i < 3; ++i) gf[i] = gb[i];
+                }
+                c.nHatf[f] = normalFlux(gf, f);
+            }
+        // fvc::div(nHatf_) = fvc::surfaceIntegrate: owner +=, neighbour -=, boundary +=, /V; K_ = -(...)
+        Fld div(nC, 0.0);
+        for (int32_t f = 0; f < c.nIF; ++f) {
+            div[c.owner[f]] += c.nHatf[f];
+            div[c.neighbour[f]] -= c.nHatf[f];
+        }
+        for (int32_t f = c.nIF; f < c.nFaces; ++f) div[c.owner[f]] += c.nHatf[f];
+        for (int32_t cc = 0; cc < nC; ++cc) K[cc] = -(div[cc] / c.V[cc]);
+        for (int p = 0; p < c.nPatches; ++p) {
+            if (coupled(p)) continue;  // processor patches: neighbour rank's cell value, by halo
+            for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) K[nC + f - c.nIF] = K[c.owner[f]];
+        }
+        c.set[SSAM_F_CURVATURE] = true;
+    }
+    return 0;
+}
+
+// interfaceProperties constructor: deltaN_ = 1e-8/pow(average(alpha1.mesh().V()), 1.0/3.0)
+double interfaceDeltaN(const std::vector<const Case*>& ranks) {
+    double sum = 0;
+    long long n = 0;
+    for (const Case* c : ranks) {
+        double s = 0;
+        for (int32_t i = 0; i < c->nCells; ++i) s += c->V[i];
+        sum += s;
+        n += c->nCells;
+    }
+    return 1e-8 / libmPow(sum / double(n), 1.0 / 3.0);
+}
+
+// ================================================================================================
 // fluid/calculateStrain.H:1-35,77-94 (the explicit stress / strain post-processing)
 // ================================================================================================
 // OpenFOAM tensor semantics restated: T() transpose, tr = xx+yy+zz, Tensor - SphericalTensor touches the
@@ -1008,6 +1140,13 @@ int orc_friction_correct(orc_case* h, const ssam_stick_params* p, const double* 
 void orc_friction_patch_centre(orc_case* h, double* centre3, double* area) {
     std::memcpy(centre3, CASE(h).fricCentre, 3 * sizeof(double));
     *area = CASE(h).fricArea;
+}
+int orc_interface_correct(orc_case* h, double deltaN, int stage) { return interfaceCorrect(CASE(h), deltaN, stage); }
+double* orc_interface_nhatf(orc_case* h) { return CASE(h).nHatf.data(); }
+double orc_interface_delta_n(orc_case** cases, int nRanks) {
+    std::vector<const Case*> v;
+    for (int r = 0; r < nRanks; ++r) v.push_back(&CASE(cases[r]));
+    return interfaceDeltaN(v);
 }
 int orc_update(orc_case* h, const ssam_update_params* p, const double* sums, int form) {
     return update(CASE(h), *p, sums, form);

@@ -46,6 +46,11 @@ def lib():
             getattr(L, "orc_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams), C.c_int]
+        L.orc_interface_correct.argtypes = [vp, C.c_double, C.c_int]
+        L.orc_interface_nhatf.restype = dp
+        L.orc_interface_nhatf.argtypes = [vp]
+        L.orc_interface_delta_n.restype = C.c_double
+        L.orc_interface_delta_n.argtypes = [C.POINTER(vp), C.c_int]
         L.orc_friction_patch_sums.argtypes = [vp, C.c_int, dp]
         L.orc_friction_correct.argtypes = [vp, C.POINTER(P.StickParams), dp, C.c_int]
         L.orc_friction_patch_centre.argtypes = [vp, dp, dp]
@@ -138,6 +143,13 @@ class OracleCase:
     def stress_strain(self, p, form=FAITHFUL):
         self._chk(lib().orc_stress_strain(self.h, C.byref(p), form))
 
+    def interface_correct(self, deltaN, stage=3):
+        """interfaceProperties::correct(); stage 1 = cell gradient, 2 = the rest (halo steps go in between)."""
+        self._chk(lib().orc_interface_correct(self.h, deltaN, stage))
+
+    def nhatf(self):
+        return np.ctypeslib.as_array(lib().orc_interface_nhatf(self.h), shape=(self.mesh.nFaces,)).copy()
+
     def friction_patch_sums(self, patch):
         out = np.zeros(4)
         lib().orc_friction_patch_sums(self.h, patch, out.ctypes.data_as(C.POINTER(C.c_double)))
@@ -173,6 +185,22 @@ def halo_exchange(cases, field):
     st = lib().orc_halo_exchange(arr, len(cases), field)
     if st:
         raise OracleError(st, "halo exchange: processor patches do not match")
+
+
+def interface_delta_n(cases):
+    arr = (C.c_void_p * len(cases))(*[c.h for c in cases])
+    return lib().orc_interface_delta_n(arr, len(cases))
+
+
+def interface_correct_multi(cases, deltaN):
+    """Decomposed interfaceProperties::correct(): processor-patch evaluations between the stages."""
+    halo_exchange(cases, P.F_ALPHA1)
+    for c in cases:
+        c.interface_correct(deltaN, 1)
+    halo_exchange(cases, P.F_GRADALPHA)
+    for c in cases:
+        c.interface_correct(deltaN, 2)
+    halo_exchange(cases, P.F_CURVATURE)
 
 
 def update_multi(cases, p, form=FAITHFUL):

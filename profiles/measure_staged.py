@@ -41,6 +41,8 @@ def main():
         "ssam_mixture_cp": (lambda: ctx.mixture("cp", p.mix), 16 * n),
         "ssam_friction_correct (qvisc + qfric)": (lambda: ctx.friction_correct(p.stick), 24 * n),
         "ssam_stress_strain (calculateStrain.H, incl. its fvc::grad)": (lambda: ctx.stress_strain(ss), grad_bytes + 72 * nc + (72 + 32 + 48) * n),
+        "ssam_interface_correct (interfaceProperties::correct: gradAlpha, nHatf, K)": (
+            lambda: ctx.interface_correct(1e-5), 92 * nif + 80 * nc + 60 * nb),
         "ssam_update_fused": (lambda: ctx.update_fused(p, 0), case.bytes_per_update),
     }
     peak = 6538.9

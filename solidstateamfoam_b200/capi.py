@@ -22,7 +22,8 @@ SYMBOLS = [
     "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
-    "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
+    "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_interface_correct",
+    "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
 ]
 
@@ -80,6 +81,11 @@ def load():
         getattr(L, "ssam_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams)]
+    L.ssam_interface_correct.argtypes = [vp, C.c_double, C.c_uint32]
+    L.ssam_interface_nhatf_download.argtypes = [vp, dp, dp]
+    L.ssam_interface_nhatf_device_ptr.restype = C.c_void_p
+    L.ssam_interface_nhatf_device_ptr.argtypes = [vp]
+    L.ssam_interface_delta_n.argtypes = [vp, dp]
     L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
@@ -238,6 +244,21 @@ class Context:
 
     def stress_strain(self, p: P.StressStrainParams):
         self._chk(self.L.ssam_stress_strain(self.h, C.byref(p)))
+
+    def interface_correct(self, deltaN: float, flags: int = 0):
+        """interfaceProperties::correct(): GRADALPHA, nHatf, CURVATURE from ALPHA1."""
+        self._chk(self.L.ssam_interface_correct(self.h, deltaN, flags))
+
+    def nhatf(self, n_internal_faces: int, n_boundary_faces: int) -> np.ndarray:
+        out = np.zeros(n_internal_faces + n_boundary_faces)
+        bi = out[n_internal_faces:]
+        self._chk(self.L.ssam_interface_nhatf_download(self.h, _dptr(out), _dptr(bi) if n_boundary_faces else None))
+        return out
+
+    def interface_delta_n(self) -> float:
+        d = C.c_double()
+        self._chk(self.L.ssam_interface_delta_n(self.h, C.byref(d)))
+        return d.value
 
     def friction_correct(self, p: P.StickParams):
         self._chk(self.L.ssam_friction_correct(self.h, C.byref(p)))

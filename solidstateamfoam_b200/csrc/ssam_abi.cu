@@ -50,6 +50,8 @@ struct ssam_ctx {
     double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
     unsigned char* bndFlags = nullptr;
     double* gradB[9] = {nullptr};
+    double* nHatf = nullptr;  // interfaceProperties::nHatf_ (surfaceScalarField, nFaces values), lazily allocated
+    double sumV = 0.0;        // sequential sum of the cell volumes (deltaN_)
 
     double* plane[SSAM_F_COUNT][9] = {{nullptr}};
     bool isSet[SSAM_F_COUNT] = {false};
@@ -85,7 +87,7 @@ namespace {
 
 thread_local std::string g_globalErr;
 
-int ncompOf(int f) { return f == SSAM_F_U ? 3 : (f == SSAM_F_GRADU ? 9 : 1); }
+int ncompOf(int f) { return (f == SSAM_F_U || f == SSAM_F_GRADALPHA) ? 3 : (f == SSAM_F_GRADU ? 9 : 1); }
 
 ssam_status fail(ssam_ctx* c, ssam_status st, const std::string& msg) {
     if (c)
@@ -181,6 +183,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->tileListInterior);
     devFree(c->tileListCoupled);
     devFree(c->V);
+    devFree(c->nHatf);
     devFree(c->magSf_b);
     devFree(c->deltaCoeffs_b);
     for (auto& p : c->Cpl) devFree(p);
@@ -550,6 +553,8 @@ ssam_status launchCellsTiled(ssam_ctx* ctx, const UpdateArgs& a, int model1, con
         SSAM_TILED(SSAM_VISC_SHEPPARD_WRIGHT)
         SSAM_TILED(SSAM_VISC_FKS)
         SSAM_TILED(SSAM_VISC_NORTON_HOFF)
+        SSAM_TILED(TILED_GRAD)
+        SSAM_TILED(TILED_STRAIN)
     }
 #undef SSAM_TILED
     return fail(ctx, SSAM_ERR_UNKNOWN_MODEL, "Unknown viscosityModel type");
@@ -560,18 +565,29 @@ ssam_status gradOrStrain(ssam_ctx* ctx, bool strain, double factor, int outField
     TRY(need(ctx, SSAM_F_U, "U"));
     UpdateArgs a;
     fillMeshArgs(ctx, a);
+    a.pfDist = ctx->pfDist;
+    a.pfDistU = a.pfDist + ctx->bandwidthTiles;
+    const bool tiled = ctx->cellKernel == 1;
     if (strain) {
         TRY(ensureField(ctx, outField));
         a.strainOut = ctx->plane[outField][0];
         a.strainFactor = factor;
-        TRY((launchCellsBoundary<MODE_STRAIN>(ctx, a, SSAM_VISC_NEWTONIAN, false)));
+        if (tiled) {
+            TRY(launchCellsTiled(ctx, a, TILED_STRAIN, ctx->tileOrder, ctx->nTiles, ctx->stream));
+        } else {
+            TRY((launchCellsBoundary<MODE_STRAIN>(ctx, a, SSAM_VISC_NEWTONIAN, false)));
+        }
         if (ctx->nProcPatches) TRY(haloExchangeField(ctx, outField));
         TRY((launchCellsBoundary<MODE_STRAIN>(ctx, a, SSAM_VISC_NEWTONIAN, true)));
         ctx->isSet[outField] = true;
     } else {
         TRY(ensureField(ctx, SSAM_F_GRADU));
         for (int k = 0; k < 9; ++k) a.gradU[k] = ctx->plane[SSAM_F_GRADU][k];
-        TRY((launchCellsBoundary<MODE_GRAD>(ctx, a, SSAM_VISC_NEWTONIAN, false)));
+        if (tiled) {
+            TRY(launchCellsTiled(ctx, a, TILED_GRAD, ctx->tileOrder, ctx->nTiles, ctx->stream));
+        } else {
+            TRY((launchCellsBoundary<MODE_GRAD>(ctx, a, SSAM_VISC_NEWTONIAN, false)));
+        }
         if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_GRADU));
         TRY((launchCellsBoundary<MODE_GRAD>(ctx, a, SSAM_VISC_NEWTONIAN, true)));
         ctx->isSet[SSAM_F_GRADU] = true;
@@ -827,6 +843,8 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     }
     TRY(devAlloc(ctx, &ctx->V, nC + 4));
     CU(cudaMemcpyAsync(ctx->V, m->V, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->sumV = 0.0;
+    for (size_t i = 0; i < nC; ++i) ctx->sumV += m->V[i];  // Foam::sum order; used by ssam_interface_delta_n
     TRY(devAlloc(ctx, &ctx->magSf_b, nB));
     TRY(devAlloc(ctx, &ctx->deltaCoeffs_b, nB));
     if (nB) {
@@ -1146,6 +1164,79 @@ ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p
     LAUNCH((k_map<StressStrainStage>), mapGrid(ctx), 256, ctx->nTot, s);
     for (int f : outs) ctx->isSet[f] = true;
     return finish(ctx);
+}
+
+// interfaceProperties::correct() -> calculateK()  (immiscibleIncompressibleTwoPhaseThermalMixture.H:80)
+ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(ensureField(ctx, SSAM_F_GRADALPHA));
+    TRY(ensureField(ctx, SSAM_F_CURVATURE));
+    if (!ctx->nHatf) TRY(devAlloc(ctx, &ctx->nHatf, size_t(ctx->nFaces)));
+    IfaceArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nCells = ctx->nCells;
+    a.nIF = ctx->nIF;
+    a.nBnd = ctx->nBnd;
+    a.geo = ctx->geo;
+    a.owner = ctx->owner;
+    a.neighbour = ctx->neighbour;
+    a.ownerStart = ctx->ownerStart;
+    a.extraStart = ctx->extraStart;
+    a.extra = ctx->extra;
+    a.V = ctx->V;
+    a.magSf_b = ctx->magSf_b;
+    a.deltaCoeffs_b = ctx->deltaCoeffs_b;
+    a.bndFlags = ctx->bndFlags;
+    a.alpha = ctx->plane[SSAM_F_ALPHA1][0];
+    for (int k = 0; k < 3; ++k) a.g[k] = ctx->plane[SSAM_F_GRADALPHA][k];
+    a.nHatf = ctx->nHatf;
+    a.K = ctx->plane[SSAM_F_CURVATURE][0];
+    a.deltaN = deltaN;
+    const int gc = gridFor(ctx->nCells, 256), gb = gridFor(ctx->nBnd, 128), gf = gridFor(ctx->nFaces, 256);
+    if (ctx->nProcPatches && (flags & 2)) TRY(haloExchangeField(ctx, SSAM_F_ALPHA1));
+    LAUNCH(k_iface_grad_cells, gc, 256, a);
+    if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_GRADALPHA));
+    if (ctx->nBnd) LAUNCH(k_iface_grad_bnd, gb, 128, a);
+    LAUNCH(k_iface_nhatf, gf, 256, a);
+    LAUNCH(k_iface_div_cells, gc, 256, a);
+    if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_CURVATURE));
+    ctx->isSet[SSAM_F_GRADALPHA] = ctx->isSet[SSAM_F_CURVATURE] = true;
+    return finish(ctx);
+}
+
+ssam_status ssam_interface_nhatf_download(ssam_ctx* ctx, double* internal_faces, double* boundary_faces) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CHECK(ctx->nHatf && ctx->isSet[SSAM_F_CURVATURE], SSAM_ERR_MISSING_FIELD,
+          "field not available: nHatf (call ssam_interface_correct first)");
+    if (internal_faces && ctx->nIF)
+        CU(cudaMemcpyAsync(internal_faces, ctx->nHatf, size_t(ctx->nIF) * sizeof(double), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    if (boundary_faces && ctx->nBnd)
+        CU(cudaMemcpyAsync(boundary_faces, ctx->nHatf + ctx->nIF, size_t(ctx->nBnd) * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
+double* ssam_interface_nhatf_device_ptr(ssam_ctx* ctx) { return ctx ? ctx->nHatf : nullptr; }
+
+ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN) {
+    CHECK(ctx && deltaN, SSAM_ERR_INVALID, "null argument");
+    CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    double sn[2] = {ctx->sumV, double(ctx->nCells)};
+    if (ctx->comm && ctx->nRanks > 1) {
+        // gAverage: sum and count over all ranks
+        double* tmp = nullptr;
+        TRY(devAlloc(ctx, &tmp, 2));
+        CU(cudaMemcpyAsync(tmp, sn, sizeof(sn), cudaMemcpyHostToDevice, ctx->stream));
+        NC(nccl().AllReduce(tmp, tmp, 2, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+        CU(cudaMemcpyAsync(sn, tmp, sizeof(sn), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    *deltaN = 1e-8 / std::pow(sn[0] / sn[1], 1.0 / 3.0);
+    return SSAM_OK;
 }
 
 ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p) {

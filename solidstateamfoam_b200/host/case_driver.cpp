@@ -165,7 +165,7 @@ int main(int argc, char** argv) {
         // ---- write the AUTO_WRITE fields ----
         std::ofstream out(outPath, std::ios::binary);
         std::vector<int> outs = {SSAM_F_EPSDOT, SSAM_F_NU1, SSAM_F_NU2, SSAM_F_NU, SSAM_F_MUEFF, SSAM_F_CP, SSAM_F_K,
-                                 SSAM_F_RHO_SOLVER, SSAM_F_RHOCP};
+                                 SSAM_F_RHO_SOLVER, SSAM_F_RHOCP, SSAM_F_CURVATURE};
         if (hasSigmay) {
             outs.push_back(SSAM_F_SIGMAF);
             outs.push_back(SSAM_F_SIGMAY);
@@ -185,6 +185,7 @@ int main(int argc, char** argv) {
             const char* foamNames[SSAM_F_COUNT] = {"U", "temp", "alpha1", "p", "epsilonDotEq", "nu1", "nu2", "sigmaf",
                                                     "sigmay", "nu", "muEff", "rho", "cp", "k", "qvisc", "qfric",
                                                     "gradU", "strainRate", "rho", "rhoCp"};
+            foamNames[SSAM_F_CURVATURE] = "interfaceProperties:K";
             for (int f : outs) {
                 std::vector<double> fi, fb;
                 volScalarFieldRef{&mesh, f}.download(fi, fb);

@@ -205,6 +205,24 @@ void volScalarFieldRef::download(std::vector<double>& internal, std::vector<doub
     mesh->check(ssam_field_download(mesh->ctx(), field, internal.data(), boundary.data()), "ssam_field_download");
 }
 
+// ---- interfaceProperties -------------------------------------------------------------------------------------------
+double interfaceProperties::deltaN() const {
+    if (deltaN_ < 0) imesh_.check(ssam_interface_delta_n(imesh_.ctx(), &deltaN_), "interfaceProperties::deltaN");
+    return deltaN_;
+}
+
+void interfaceProperties::correct() {
+    imesh_.check(ssam_interface_correct(imesh_.ctx(), deltaN(), 0), "interfaceProperties::correct");
+}
+
+void interfaceProperties::nHatf(std::vector<double>& internalFaces, std::vector<double>& boundaryFaces,
+                                int nInternalFaces) const {
+    internalFaces.resize(size_t(nInternalFaces));
+    boundaryFaces.resize(size_t(imesh_.nBoundaryFaces()));
+    imesh_.check(ssam_interface_nhatf_download(imesh_.ctx(), internalFaces.data(), boundaryFaces.data()),
+                 "interfaceProperties::nHatf");
+}
+
 // ---- viscosityModel ------------------------------------------------------------------------------------------------
 std::map<word, viscosityModel::ctor>& viscosityModel::dictionaryConstructorTable() {
     static std::map<word, ctor> table = {

@@ -9,7 +9,8 @@ from oracle import pyoracle as O
 from solidstateamfoam_b200 import params as P
 
 REL_TOL = 1e-11  # BASELINE.json north_star: every floating-point field within 1e-11 relative per cell
-BIT_EXACT = (P.F_GRADU, P.F_EPSDOT, P.F_STRAINRATE, P.F_RHO, P.F_CP, P.F_NU2, P.F_RHO_SOLVER, P.F_RHOCP, P.F_U)
+BIT_EXACT = (P.F_GRADU, P.F_EPSDOT, P.F_STRAINRATE, P.F_RHO, P.F_CP, P.F_NU2, P.F_RHO_SOLVER, P.F_RHOCP, P.F_U,
+             P.F_GRADALPHA, P.F_CURVATURE)
 
 EPS_FACTOR = math.sqrt(2.0 / 3.0)
 SR_FACTOR = math.sqrt(2.0)

@@ -109,6 +109,16 @@ def main():
     ctx.grad_u()
     gi, gb = ctx.download(P.F_GRADU)
     check_field("staged gradU", np.concatenate([gi, gb]), oc.field(P.F_GRADU), True)
+    # interfaceProperties::correct() across ranks: halos of alpha1, gradAlpha and K
+    dn = ctx.interface_delta_n()
+    assert abs(dn - O.interface_delta_n(ocs)) <= 1e-15 * dn
+    dn = O.interface_delta_n(ocs)
+    O.interface_correct_multi(ocs, dn)
+    ctx.interface_correct(dn, capi.FUSED_HALO_INPUTS)
+    for f in (P.F_GRADALPHA, P.F_CURVATURE):
+        gi, gb = ctx.download(f)
+        check_field(f"rank{rank} {P.FIELD_NAMES[f]}", np.concatenate([gi, gb]), oc.field(f), True)
+    assert np.array_equal(ctx.nhatf(case.mesh.nInternalFaces, case.mesh.nBoundaryFaces), oc.nhatf())
     n_proc = int(sum(case.mesh.patchSize[p] for p in range(case.mesh.nPatches) if case.mesh.patchKind[p] == 1))
     dist.barrier()
     print(f"[rank {rank}/{world}] {args.decomp}: {case.mesh.nCells} cells, {n_proc} processor faces, "

@@ -279,3 +279,48 @@ def test_stress_strain_post_processing(ctx, name):
         check_field(P.FIELD_NAMES[f], np.concatenate([gi, gb]), oc.field(f), f in (P.F_GRADU, P.F_DEPSEQ, P.F_EPSEQ))
     gi, gb = ctx.download(P.F_SIGMAVM)
     assert np.array_equal(np.concatenate([gi, gb]), oc.field(P.F_SIGMAVM))  # pure IEEE arithmetic
+
+
+@pytest.mark.parametrize("name", ["cfg1_hex", "cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly"])
+def test_interface_correct_matches_oracle(ctx, name):
+    """interfaceProperties::correct() (SURVEY 8f-2): gradAlpha, nHatf, K -- pure IEEE arithmetic in the
+    reference's summation order, so every value is bit-exact."""
+    case = small_cases()[name]()
+    m = case.mesh
+    ctx.load_case(case)
+    oc = oracle_case(case, apply_bc=False)
+    dn = ctx.interface_delta_n()
+    assert dn == O.interface_delta_n([oc])
+    ctx.interface_correct(dn)
+    oc.interface_correct(dn)
+    for f in (P.F_GRADALPHA, P.F_CURVATURE):
+        gi, gb = ctx.download(f)
+        check_field(P.FIELD_NAMES[f], np.concatenate([gi, gb]), oc.field(f), True)
+    assert np.array_equal(ctx.nhatf(m.nInternalFaces, m.nBoundaryFaces), oc.nhatf())
+    assert np.count_nonzero(oc.internal(P.F_CURVATURE)) > 0
+
+
+def test_interface_curvature_of_a_sphere(ctx):
+    """analytic pin on the GPU itself: K = 2/R on a spherical tanh interface"""
+    n = 40
+    m = M.hex_block(n, n, n, origin=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0))
+    R, width = 0.6, 3.0 * 2.0 / n
+    xc = np.concatenate([m.C, m.Cf[m.nInternalFaces:]])
+    r = np.sqrt((xc ** 2).sum(1))
+    a = 0.5 * (1.0 - np.tanh((r - R) / width))
+    ctx.mesh_set(m)
+    ctx.upload(P.F_ALPHA1, a[: m.nCells], a[m.nCells:])
+    ctx.interface_correct(ctx.interface_delta_n())
+    K, _ = ctx.download(P.F_CURVATURE)
+    rc = r[: m.nCells]
+    band = np.abs(rc - R) < 0.5 * width
+    assert np.allclose(K[band] * rc[band], 2.0, rtol=0.06)
+
+
+def test_interface_requires_alpha(ctx):
+    ctx.mesh_set(M.hex_block(3, 3, 3))
+    with pytest.raises(capi.SsamError) as e:
+        ctx.interface_correct(1e-7)
+    assert e.value.status == P.ERR_MISSING_FIELD
+    with pytest.raises(capi.SsamError):
+        ctx.nhatf(54, 54)

@@ -44,10 +44,13 @@ def oracle_sequence(case, steps=2, U=None):
     p = case.params
     nh = p.visc1.model == P.VISC_NORTON_HOFF
 
+    dn = O.interface_delta_n([oc])
+
     def thermo_correct():
         oc.viscosity_correct(1, p.visc1)
         oc.viscosity_correct(2, p.visc2)
         oc.mixture("calc_nu", p.mix)
+        oc.interface_correct(dn)  # interfaceProperties::correct(), immiscible...H:80
 
     thermo_correct()  # constructors
     for _ in range(steps):

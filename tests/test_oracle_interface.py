@@ -1,0 +1,111 @@
+"""interfaceProperties::correct() restatement pinned by analytic cases (CPU only).
+
+The class is OpenFOAM library code, absent from the reference tree and not compilable here, so -- like the
+rest of the oracle -- it is pinned by closed-form answers rather than by reference output: a linear alpha
+field (exact gradient, zero curvature), a spherical interface (K = 2/R), a cylinder (K = 1/R), and the
+decomposed evaluation agreeing with the serial one.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from solidstateamfoam_b200 import mesh as M
+from solidstateamfoam_b200 import params as P
+
+
+def _case(m, alpha_fn):
+    oc = O.OracleCase(m)
+    xc = np.concatenate([m.C, m.Cf[m.nInternalFaces:]])
+    a = alpha_fn(xc)
+    oc.set(P.F_ALPHA1, a[: m.nCells], a[m.nCells:])
+    return oc
+
+
+def test_delta_n():
+    m = M.hex_block(6, 5, 4, length=(0.6, 0.5, 0.4))
+    oc = O.OracleCase(m)
+    d = O.interface_delta_n([oc])
+    assert d == pytest.approx(1e-8 / 0.1, rel=1e-13)  # cube root of the 0.001 cell volume
+
+
+def test_linear_alpha_gives_exact_gradient_and_zero_curvature():
+    m = M.hex_block(10, 8, 6, length=(1.0, 0.8, 0.6))
+    a = np.array([0.3, -0.2, 0.5])
+    oc = _case(m, lambda x: 0.4 + x @ a)
+    dn = O.interface_delta_n([oc])
+    oc.interface_correct(dn)
+    g = oc.field(P.F_GRADALPHA)
+    assert np.allclose(g, a, rtol=0, atol=1e-12)  # cells and (corrected) boundary values
+    nh = oc.nhatf()
+    assert np.allclose(nh, (m.Sf @ a) / np.linalg.norm(a), rtol=1e-6, atol=1e-15)  # deltaN/|grad alpha| ~ 2e-7
+    K = oc.internal(P.F_CURVATURE)
+    assert np.abs(K).max() < 1e-9
+    # boundary values of K: the adjacent cell's value
+    assert np.array_equal(oc.boundary(P.F_CURVATURE), K[m.owner[m.nInternalFaces:]])
+
+
+@pytest.mark.parametrize("shape,expect", [("sphere", 2.0), ("cylinder", 1.0)])
+def test_curvature_of_sphere_and_cylinder(shape, expect):
+    n = 40
+    m = M.hex_block(n, n, n, origin=(-1.0, -1.0, -1.0), length=(2.0, 2.0, 2.0))
+    R, width = 0.6, 3.0 * 2.0 / n
+
+    def radius(x):
+        return np.sqrt((x[:, :2] ** 2).sum(1)) if shape == "cylinder" else np.sqrt((x ** 2).sum(1))
+
+    oc = _case(m, lambda x: 0.5 * (1.0 - np.tanh((radius(x) - R) / width)))
+    oc.interface_correct(O.interface_delta_n([oc]))
+    r = radius(m.C)
+    band = np.abs(r - R) < 0.5 * width
+    if shape == "cylinder":
+        band &= np.abs(m.C[:, 2]) < 0.7
+    K = oc.internal(P.F_CURVATURE)[band]
+    assert band.sum() > 500
+    # K = -div(nHat), nHat = grad(alpha)/|grad(alpha)| pointing into phase 1 (the inside): K = +(d-1)/r
+    assert np.allclose(K * r[band], expect, rtol=0.06)  # second-order scheme on a 40^3 grid
+    assert abs((K * r[band]).mean() - expect) < 0.02 * expect
+    # unit normals: |nHatf| <= |Sf|
+    assert (np.abs(oc.nhatf()) <= m.magSf * (1 + 1e-12)).all()
+
+
+def test_sharp_step_has_no_nan():
+    m = M.hex_block(8, 8, 8)
+    oc = _case(m, lambda x: (x[:, 2] < 0.5 * x[:, 2].max()).astype(float))
+    oc.interface_correct(O.interface_delta_n([oc]))
+    for f in (P.F_GRADALPHA, P.F_CURVATURE):
+        assert np.isfinite(oc.field(f)).all()
+    assert np.isfinite(oc.nhatf()).all()
+    g = oc.internal(P.F_GRADALPHA)
+    assert (g[:, 2] <= 0).all() and np.count_nonzero(g[:, 2]) == 2 * 64  # the two cell layers at the step
+
+
+def test_decomposed_equals_serial():
+    dims = (10, 8, 12)
+    L = (1.0, 0.8, 1.2)
+    h = M.hex_block(*dims, length=L, affine=(1.0, 0.2, 0.1, 0.0, 1.0, 0.15, 0.0, 0.0, 1.0), _keep=True)
+
+    def alpha(x):
+        return 0.5 * (1.0 - np.tanh((np.sqrt(((x - 0.55) ** 2).sum(1)) - 0.35) / 0.2))
+
+    rng = np.random.default_rng(3)
+    nc = dims[0] * dims[1] * dims[2]
+    cell_proc = rng.integers(0, 3, size=nc // 8 + 1)[np.arange(nc) // 8]
+    whole, parts = M.decompose(h, cell_proc, 3)
+    serial = _case(whole, alpha)
+    dn = O.interface_delta_n([serial])
+    serial.interface_correct(dn)
+    ocs = [_case(p, alpha) for p in parts]
+    assert O.interface_delta_n(ocs) == pytest.approx(dn, rel=1e-14)
+    O.interface_correct_multi(ocs, dn)
+    Ks, Gs = serial.internal(P.F_CURVATURE), serial.internal(P.F_GRADALPHA)
+    for r, (oc, p) in enumerate(zip(ocs, parts)):
+        cells = np.nonzero(cell_proc == r)[0]  # decomposePar keeps the global cell order within a rank
+        assert np.array_equal(p.C, whole.C[cells])
+        assert np.allclose(oc.internal(P.F_GRADALPHA), Gs[cells], rtol=1e-11, atol=1e-12)
+        assert np.allclose(oc.internal(P.F_CURVATURE), Ks[cells], rtol=1e-9, atol=1e-8)
+        # processor-patch boundary values are the neighbour rank's cell values
+        for q in range(p.nPatches):
+            if p.patchKind[q] != 1:
+                continue
+            s = slice(p.patchStart[q] - p.nInternalFaces, p.patchStart[q] - p.nInternalFaces + p.patchSize[q])
+            assert np.isfinite(oc.boundary(P.F_CURVATURE)[s]).all()
