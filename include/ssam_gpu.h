@@ -286,6 +286,25 @@ SSAM_API ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_
  * No alphaContactAngle patches (the reference's cases have none): correctContactAngle is a no-op.
  * nHatf_ is a surfaceScalarField (alphaEqn.H:154 `phic*thermo.nHatf()`): nInternalFaces + nBoundaryFaces values. */
 SSAM_API ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags);
+
+/* ---- surfaceScalarFields: nInternalFaces values, then nBoundaryFaces values in patch order --------- */
+enum {
+    SSAM_FF_NHATF = 0, /* interfaceProperties::nHatf_                                                   */
+    SSAM_FF_MUF = 1,   /* incompressibleTwoPhaseThermalMixture::muf()  (…Mixture.C:163-180)              */
+    SSAM_FF_NUF = 2,   /* incompressibleTwoPhaseThermalMixture::nuf()  (…Mixture.C:183-202)              */
+    SSAM_FF_COUNT = 3
+};
+SSAM_API ssam_status ssam_face_field_download(ssam_ctx* ctx, int face_field, double* internal_faces,
+                                              double* boundary_faces);
+SSAM_API double* ssam_face_field_device_ptr(ssam_ctx* ctx, int face_field);
+/* muf()/nuf(): alpha1f = min(max(fvc::interpolate(alpha1),0),1);
+ *   muf = alpha1f*rho1*interpolate(nu1) + (1-alpha1f)*rho2*interpolate(nu2);  nuf = muf/(alpha1f*rho1+(1-alpha1f)*rho2)
+ * linear interpolation; reads ALPHA1, NU1, NU2 (processor-patch boundary values as left by the last update). */
+SSAM_API ssam_status ssam_mixture_muf(ssam_ctx* ctx, const ssam_mixture_params* p);
+SSAM_API ssam_status ssam_mixture_nuf(ssam_ctx* ctx, const ssam_mixture_params* p);
+/* min(vf).value(), max(vf).value() over internal and boundary values and over all ranks, as printed by
+ * fluid/TEqn.H:42-43 ("Min/max T"); scalar fields only. Synchronises the stream. */
+SSAM_API ssam_status ssam_field_min_max(ssam_ctx* ctx, int field, double* min_value, double* max_value);
 SSAM_API ssam_status ssam_interface_nhatf_download(ssam_ctx* ctx, double* internal_faces, double* boundary_faces);
 SSAM_API double* ssam_interface_nhatf_device_ptr(ssam_ctx* ctx);
 /* deltaN_ = 1e-8/pow(average(mesh.V()), 1.0/3.0) (interfaceProperties constructor); average over all ranks

@@ -52,6 +52,7 @@ struct Case {
         haloOffsets, fricCells, faceColour;
     bool addrBuilt = false;
     Fld nHatf;  // surfaceScalarField: internal faces then boundary faces
+    Fld muf, nuf;
 };
 
 int ncompOf(int field) {
@@ -506,6 +507,37 @@ int mixtureMu(Case& c, const ssam_mixture_params& p, int form) {
 }
 
 // :46-53  nu_ = mu()/(limitedAlpha1*rho1_ + (scalar(1) - limitedAlpha1)*rho2_)
+// fvc::interpolate(vf) with the linear scheme (surfaceInterpolationScheme::interpolate restated)
+Fld interpolateLinear(const Case& c, const Fld& vf) {
+    Fld sf(c.nFaces);
+    for (int32_t f = 0; f < c.nIF; ++f) sf[f] = c.w[f] * (vf[c.owner[f]] - vf[c.neighbour[f]]) + vf[c.neighbour[f]];
+    for (int p = 0; p < c.nPatches; ++p)
+        for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) {
+            const double vb = vf[c.nCells + (f - c.nIF)];
+            sf[f] = (c.patchKind[p] == SSAM_PATCH_PROCESSOR) ? c.w[f] * vf[c.owner[f]] + (1.0 - c.w[f]) * vb : vb;
+        }
+    return sf;
+}
+
+// muf() incompressibleTwoPhaseThermalMixture.C:163-180, nuf() :183-202
+int mixtureFaceVisc(Case& c, const ssam_mixture_params& p, bool nuf) {
+    if (!c.set[SSAM_F_ALPHA1] || !c.set[SSAM_F_NU1] || !c.set[SSAM_F_NU2]) {
+        c.err = "alpha1 / nu1 / nu2 not set";
+        return SSAM_ERR_MISSING_FIELD;
+    }
+    const Fld alpha1f = minFS(maxFS(interpolateLinear(c, c.f[SSAM_F_ALPHA1]), 0.0), 1.0);  // :166-169, :186-189
+    const Fld n1f = interpolateLinear(c, c.f[SSAM_F_NU1]), n2f = interpolateLinear(c, c.f[SSAM_F_NU2]);
+    // alpha1f*rho1_*interpolate(nu1) + (scalar(1) - alpha1f)*rho2_*interpolate(nu2)      :176-177, :197-198
+    Fld num = addFF(mulFF(mulFS(alpha1f, p.rho1), n1f), mulFF(mulFS(subSF(1.0, alpha1f), p.rho2), n2f));
+    if (!nuf) {
+        c.muf = num;
+        return 0;
+    }
+    // /(alpha1f*rho1_ + (scalar(1) - alpha1f)*rho2_)                                      :199
+    c.nuf = divFF(num, addFF(mulFS(alpha1f, p.rho1), mulFS(subSF(1.0, alpha1f), p.rho2)));
+    return 0;
+}
+
 int mixtureCalcNu(Case& c, const ssam_mixture_params& p, int form) {
     if (int e = needNu(c)) return e;
     Fld& nu = fieldRef(c, SSAM_F_NU);
@@ -1140,6 +1172,26 @@ int orc_friction_correct(orc_case* h, const ssam_stick_params* p, const double* 
 void orc_friction_patch_centre(orc_case* h, double* centre3, double* area) {
     std::memcpy(centre3, CASE(h).fricCentre, 3 * sizeof(double));
     *area = CASE(h).fricArea;
+}
+int orc_mixture_face_visc(orc_case* h, const ssam_mixture_params* p, int nuf) { return mixtureFaceVisc(CASE(h), *p, nuf != 0); }
+double* orc_face_field(orc_case* h, int which) {
+    Case& c = CASE(h);
+    return which == SSAM_FF_NHATF ? c.nHatf.data() : (which == SSAM_FF_MUF ? c.muf.data() : c.nuf.data());
+}
+// min(vf).value(), max(vf).value() (fluid/TEqn.H:42-43): over internal and boundary values
+void orc_field_min_max(orc_case** cases, int nRanks, int field, double* mn, double* mx) {
+    double lo = 0, hi = 0;
+    bool first = true;
+    for (int r = 0; r < nRanks; ++r) {
+        const Case& c = CASE(cases[r]);
+        for (double v : c.f[field]) {
+            if (first) { lo = hi = v; first = false; }
+            lo = ofMin(lo, v);
+            hi = ofMax(hi, v);
+        }
+    }
+    *mn = lo;
+    *mx = hi;
 }
 int orc_interface_correct(orc_case* h, double deltaN, int stage) { return interfaceCorrect(CASE(h), deltaN, stage); }
 double* orc_interface_nhatf(orc_case* h) { return CASE(h).nHatf.data(); }

@@ -46,6 +46,10 @@ def lib():
             getattr(L, "orc_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams), C.c_int]
+        L.orc_mixture_face_visc.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
+        L.orc_face_field.restype = dp
+        L.orc_face_field.argtypes = [vp, C.c_int]
+        L.orc_field_min_max.argtypes = [C.POINTER(vp), C.c_int, C.c_int, dp, dp]
         L.orc_interface_correct.argtypes = [vp, C.c_double, C.c_int]
         L.orc_interface_nhatf.restype = dp
         L.orc_interface_nhatf.argtypes = [vp]
@@ -150,6 +154,12 @@ class OracleCase:
     def nhatf(self):
         return np.ctypeslib.as_array(lib().orc_interface_nhatf(self.h), shape=(self.mesh.nFaces,)).copy()
 
+    def mixture_face_visc(self, p, nuf=False):
+        """muf() / nuf(): returns the surfaceScalarField (internal faces then boundary faces)."""
+        self._chk(lib().orc_mixture_face_visc(self.h, C.byref(p), 1 if nuf else 0))
+        which = P.FF_NUF if nuf else P.FF_MUF
+        return np.ctypeslib.as_array(lib().orc_face_field(self.h, which), shape=(self.mesh.nFaces,)).copy()
+
     def friction_patch_sums(self, patch):
         out = np.zeros(4)
         lib().orc_friction_patch_sums(self.h, patch, out.ctypes.data_as(C.POINTER(C.c_double)))
@@ -185,6 +195,13 @@ def halo_exchange(cases, field):
     st = lib().orc_halo_exchange(arr, len(cases), field)
     if st:
         raise OracleError(st, "halo exchange: processor patches do not match")
+
+
+def field_min_max(cases, field):
+    arr = (C.c_void_p * len(cases))(*[c.h for c in cases])
+    mn, mx = C.c_double(), C.c_double()
+    lib().orc_field_min_max(arr, len(cases), field, C.byref(mn), C.byref(mx))
+    return mn.value, mx.value
 
 
 def interface_delta_n(cases):

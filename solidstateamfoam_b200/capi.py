@@ -23,7 +23,8 @@ SYMBOLS = [
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_interface_correct",
-    "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
+    "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
+    "ssam_face_field_device_ptr", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
 ]
 
@@ -86,6 +87,12 @@ def load():
     L.ssam_interface_nhatf_device_ptr.restype = C.c_void_p
     L.ssam_interface_nhatf_device_ptr.argtypes = [vp]
     L.ssam_interface_delta_n.argtypes = [vp, dp]
+    L.ssam_face_field_download.argtypes = [vp, C.c_int, dp, dp]
+    L.ssam_face_field_device_ptr.restype = C.c_void_p
+    L.ssam_face_field_device_ptr.argtypes = [vp, C.c_int]
+    L.ssam_mixture_muf.argtypes = [vp, C.POINTER(P.MixtureParams)]
+    L.ssam_mixture_nuf.argtypes = [vp, C.POINTER(P.MixtureParams)]
+    L.ssam_field_min_max.argtypes = [vp, C.c_int, dp, dp]
     L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
@@ -254,6 +261,21 @@ class Context:
         bi = out[n_internal_faces:]
         self._chk(self.L.ssam_interface_nhatf_download(self.h, _dptr(out), _dptr(bi) if n_boundary_faces else None))
         return out
+
+    def face_field(self, which: int, n_internal_faces: int, n_boundary_faces: int) -> np.ndarray:
+        out = np.zeros(n_internal_faces + n_boundary_faces)
+        bi = out[n_internal_faces:]
+        self._chk(self.L.ssam_face_field_download(self.h, which, _dptr(out), _dptr(bi) if n_boundary_faces else None))
+        return out
+
+    def mixture_face_visc(self, p: P.MixtureParams, nuf: bool = False):
+        """muf() / nuf() -> FF_MUF / FF_NUF"""
+        self._chk((self.L.ssam_mixture_nuf if nuf else self.L.ssam_mixture_muf)(self.h, C.byref(p)))
+
+    def field_min_max(self, field: int):
+        lo, hi = C.c_double(), C.c_double()
+        self._chk(self.L.ssam_field_min_max(self.h, field, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def interface_delta_n(self) -> float:
         d = C.c_double()

@@ -50,7 +50,9 @@ struct ssam_ctx {
     double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
     unsigned char* bndFlags = nullptr;
     double* gradB[9] = {nullptr};
-    double* nHatf = nullptr;  // interfaceProperties::nHatf_ (surfaceScalarField, nFaces values), lazily allocated
+    double* faceField[SSAM_FF_COUNT] = {nullptr};  // surfaceScalarFields (nFaces values each), lazily allocated
+    bool faceFieldSet[SSAM_FF_COUNT] = {false};
+    double* minmaxScratch = nullptr;
     double sumV = 0.0;        // sequential sum of the cell volumes (deltaN_)
 
     double* plane[SSAM_F_COUNT][9] = {{nullptr}};
@@ -170,6 +172,12 @@ ssam_status ensureField(ssam_ctx* ctx, int f) {
     return SSAM_OK;
 }
 
+ssam_status ensureFaceField(ssam_ctx* ctx, int ff) {
+    CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    if (!ctx->faceField[ff]) TRY(devAlloc(ctx, &ctx->faceField[ff], size_t(ctx->nFaces)));
+    return SSAM_OK;
+}
+
 void freeMesh(ssam_ctx* c) {
     devFree(c->geo);
     devFree(c->owner);
@@ -183,7 +191,11 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->tileListInterior);
     devFree(c->tileListCoupled);
     devFree(c->V);
-    devFree(c->nHatf);
+    for (int k = 0; k < SSAM_FF_COUNT; ++k) {
+        devFree(c->faceField[k]);
+        c->faceFieldSet[k] = false;
+    }
+    devFree(c->minmaxScratch);
     devFree(c->magSf_b);
     devFree(c->deltaCoeffs_b);
     for (auto& p : c->Cpl) devFree(p);
@@ -1172,7 +1184,7 @@ ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags)
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(ensureField(ctx, SSAM_F_GRADALPHA));
     TRY(ensureField(ctx, SSAM_F_CURVATURE));
-    if (!ctx->nHatf) TRY(devAlloc(ctx, &ctx->nHatf, size_t(ctx->nFaces)));
+    TRY(ensureFaceField(ctx, SSAM_FF_NHATF));
     IfaceArgs a;
     std::memset(&a, 0, sizeof(a));
     a.nCells = ctx->nCells;
@@ -1190,7 +1202,7 @@ ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags)
     a.bndFlags = ctx->bndFlags;
     a.alpha = ctx->plane[SSAM_F_ALPHA1][0];
     for (int k = 0; k < 3; ++k) a.g[k] = ctx->plane[SSAM_F_GRADALPHA][k];
-    a.nHatf = ctx->nHatf;
+    a.nHatf = ctx->faceField[SSAM_FF_NHATF];
     a.K = ctx->plane[SSAM_F_CURVATURE][0];
     a.deltaN = deltaN;
     const int gc = gridFor(ctx->nCells, 256), gb = gridFor(ctx->nBnd, 128), gf = gridFor(ctx->nFaces, 256);
@@ -1202,24 +1214,90 @@ ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags)
     LAUNCH(k_iface_div_cells, gc, 256, a);
     if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_CURVATURE));
     ctx->isSet[SSAM_F_GRADALPHA] = ctx->isSet[SSAM_F_CURVATURE] = true;
+    ctx->faceFieldSet[SSAM_FF_NHATF] = true;
     return finish(ctx);
 }
 
-ssam_status ssam_interface_nhatf_download(ssam_ctx* ctx, double* internal_faces, double* boundary_faces) {
+ssam_status ssam_face_field_download(ssam_ctx* ctx, int ff, double* internal_faces, double* boundary_faces) {
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
-    CHECK(ctx->nHatf && ctx->isSet[SSAM_F_CURVATURE], SSAM_ERR_MISSING_FIELD,
-          "field not available: nHatf (call ssam_interface_correct first)");
+    CHECK(ff >= 0 && ff < SSAM_FF_COUNT, SSAM_ERR_INVALID, "bad face field id");
+    CHECK(ctx->faceField[ff] && ctx->faceFieldSet[ff], SSAM_ERR_MISSING_FIELD,
+          "face field not available (nHatf: ssam_interface_correct, muf/nuf: ssam_mixture_muf/nuf)");
+    const double* src = ctx->faceField[ff];
     if (internal_faces && ctx->nIF)
-        CU(cudaMemcpyAsync(internal_faces, ctx->nHatf, size_t(ctx->nIF) * sizeof(double), cudaMemcpyDeviceToHost,
-                           ctx->stream));
+        CU(cudaMemcpyAsync(internal_faces, src, size_t(ctx->nIF) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (boundary_faces && ctx->nBnd)
-        CU(cudaMemcpyAsync(boundary_faces, ctx->nHatf + ctx->nIF, size_t(ctx->nBnd) * sizeof(double),
-                           cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(boundary_faces, src + ctx->nIF, size_t(ctx->nBnd) * sizeof(double), cudaMemcpyDeviceToHost,
+                           ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
 
-double* ssam_interface_nhatf_device_ptr(ssam_ctx* ctx) { return ctx ? ctx->nHatf : nullptr; }
+double* ssam_face_field_device_ptr(ssam_ctx* ctx, int ff) {
+    return (ctx && ff >= 0 && ff < SSAM_FF_COUNT) ? ctx->faceField[ff] : nullptr;
+}
+
+static ssam_status mixtureFaceVisc(ssam_ctx* ctx, const ssam_mixture_params* p, bool nuf) {
+    CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
+    TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
+    TRY(need(ctx, SSAM_F_NU1, "nu1 (viscosityModel::correct() of phase 1)"));
+    TRY(need(ctx, SSAM_F_NU2, "nu2 (viscosityModel::correct() of phase 2)"));
+    const int ff = nuf ? SSAM_FF_NUF : SSAM_FF_MUF;
+    TRY(ensureFaceField(ctx, ff));
+    FaceViscArgs a;
+    a.nCells = ctx->nCells;
+    a.nIF = ctx->nIF;
+    a.nBnd = ctx->nBnd;
+    a.geo = ctx->geo;
+    a.owner = ctx->owner;
+    a.neighbour = ctx->neighbour;
+    a.bndFlags = ctx->bndFlags;
+    a.alpha = ctx->plane[SSAM_F_ALPHA1][0];
+    a.nu1 = ctx->plane[SSAM_F_NU1][0];
+    a.nu2 = ctx->plane[SSAM_F_NU2][0];
+    a.rho1 = p->rho1;
+    a.rho2 = p->rho2;
+    a.out = ctx->faceField[ff];
+    if (nuf) {
+        LAUNCH((k_face_visc<true>), gridFor(ctx->nFaces, 256), 256, a);
+    } else {
+        LAUNCH((k_face_visc<false>), gridFor(ctx->nFaces, 256), 256, a);
+    }
+    ctx->faceFieldSet[ff] = true;
+    return finish(ctx);
+}
+ssam_status ssam_mixture_muf(ssam_ctx* ctx, const ssam_mixture_params* p) { return mixtureFaceVisc(ctx, p, false); }
+ssam_status ssam_mixture_nuf(ssam_ctx* ctx, const ssam_mixture_params* p) { return mixtureFaceVisc(ctx, p, true); }
+
+ssam_status ssam_field_min_max(ssam_ctx* ctx, int field, double* min_value, double* max_value) {
+    CHECK(ctx && min_value && max_value, SSAM_ERR_INVALID, "null argument");
+    CHECK(field >= 0 && field < SSAM_F_COUNT && ncompOf(field) == 1, SSAM_ERR_INVALID, "scalar field id expected");
+    TRY(need(ctx, field, "min/max of a field that was never set"));
+    const int nBlocks = std::min(gridFor(ctx->nTot, 256), 148 * 8);
+    if (!ctx->minmaxScratch) TRY(devAlloc(ctx, &ctx->minmaxScratch, size_t(2 * 148 * 8 + 2)));
+    double* out = ctx->minmaxScratch + 2 * 148 * 8;
+    LAUNCH(k_minmax, nBlocks, 256, ctx->plane[field][0], ctx->nTot, ctx->minmaxScratch);
+    LAUNCH(k_minmax_final, 1, 256, ctx->minmaxScratch, nBlocks, out);
+    if (ctx->comm && ctx->nRanks > 1) {
+        NcclApi& N = nccl();
+        NC(N.GroupStart());
+        NC(N.AllReduce(out, out, 1, ncclFloat64, ncclMin, ctx->comm, ctx->stream));
+        NC(N.AllReduce(out + 1, out + 1, 1, ncclFloat64, ncclMax, ctx->comm, ctx->stream));
+        NC(N.GroupEnd());
+        ctx->launches++;
+    }
+    double h[2];
+    CU(cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *min_value = h[0];
+    *max_value = h[1];
+    return SSAM_OK;
+}
+
+ssam_status ssam_interface_nhatf_download(ssam_ctx* ctx, double* internal_faces, double* boundary_faces) {
+    return ssam_face_field_download(ctx, SSAM_FF_NHATF, internal_faces, boundary_faces);
+}
+double* ssam_interface_nhatf_device_ptr(ssam_ctx* ctx) { return ssam_face_field_device_ptr(ctx, SSAM_FF_NHATF); }
 
 ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN) {
     CHECK(ctx && deltaN, SSAM_ERR_INVALID, "null argument");

@@ -160,6 +160,9 @@ int main(int argc, char** argv) {
                 std::printf("friction.correct() skipped: no sigmay registered (NortonHoff, SURVEY D-1)\n");
             thermo.cp();                                          // TEqn.H:12
             thermo.k();                                           // TEqn.H:15
+            double tMin = 0, tMax = 0;
+            mesh.minMax(SSAM_F_T, tMin, tMax);                    // TEqn.H:42-43
+            std::printf("Min/max T:%.17g %.17g\n", tMin, tMax);
         }
 
         // ---- write the AUTO_WRITE fields ----

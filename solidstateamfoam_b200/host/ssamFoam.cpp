@@ -401,6 +401,21 @@ static void readConductivity(const dictionary& d, ssam_conductivity& k, int phas
     }
 }
 
+static void faceVisc(const fvMeshGpu& mesh, const ssam_mixture_params& mix, bool nuf, std::vector<double>& fi,
+                     std::vector<double>& fb, int nInternalFaces) {
+    mesh.check(nuf ? ssam_mixture_nuf(mesh.ctx(), &mix) : ssam_mixture_muf(mesh.ctx(), &mix), nuf ? "nuf()" : "muf()");
+    fi.resize(size_t(nInternalFaces));
+    fb.resize(size_t(mesh.nBoundaryFaces()));
+    mesh.check(ssam_face_field_download(mesh.ctx(), nuf ? SSAM_FF_NUF : SSAM_FF_MUF, fi.data(), fb.data()),
+               "ssam_face_field_download");
+}
+void incompressibleTwoPhaseThermalMixture::muf(std::vector<double>& fi, std::vector<double>& fb, int nIF) const {
+    faceVisc(mesh_, mix_, false, fi, fb, nIF);
+}
+void incompressibleTwoPhaseThermalMixture::nuf(std::vector<double>& fi, std::vector<double>& fb, int nIF) const {
+    faceVisc(mesh_, mix_, true, fi, fb, nIF);
+}
+
 void incompressibleTwoPhaseThermalMixture::readThermal() {
     // k1()/k2() look their constants up on every call (:215-223,:261)
     readConductivity(nuModel1_->viscosityProperties(), mix_.k1, 1);

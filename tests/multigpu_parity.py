@@ -119,6 +119,14 @@ def main():
         gi, gb = ctx.download(f)
         check_field(f"rank{rank} {P.FIELD_NAMES[f]}", np.concatenate([gi, gb]), oc.field(f), True)
     assert np.array_equal(ctx.nhatf(case.mesh.nInternalFaces, case.mesh.nBoundaryFaces), oc.nhatf())
+    # muf()/nuf() on processor faces, and the cross-rank "Min/max T"
+    for f in (P.F_NU1, P.F_NU2):
+        ctx.upload(f, oc.internal(f), oc.boundary(f))
+    for nuf, ff in ((False, P.FF_MUF), (True, P.FF_NUF)):
+        ctx.mixture_face_visc(case.params.mix, nuf)
+        assert np.array_equal(ctx.face_field(ff, case.mesh.nInternalFaces, case.mesh.nBoundaryFaces),
+                              oc.mixture_face_visc(case.params.mix, nuf))
+    assert ctx.field_min_max(P.F_T) == O.field_min_max(ocs, P.F_T)
     n_proc = int(sum(case.mesh.patchSize[p] for p in range(case.mesh.nPatches) if case.mesh.patchKind[p] == 1))
     dist.barrier()
     print(f"[rank {rank}/{world}] {args.decomp}: {case.mesh.nCells} cells, {n_proc} processor faces, "

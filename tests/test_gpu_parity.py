@@ -324,3 +324,42 @@ def test_interface_requires_alpha(ctx):
     assert e.value.status == P.ERR_MISSING_FIELD
     with pytest.raises(capi.SsamError):
         ctx.nhatf(54, 54)
+
+
+@pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly"])
+def test_muf_nuf_face_fields(ctx, name):
+    """incompressibleTwoPhaseThermalMixture::muf()/nuf() (…Mixture.C:163-202): IEEE-only, bit-exact given nu1/nu2"""
+    case = small_cases()[name]()
+    m = case.mesh
+    ctx.load_case(case)
+    ctx.update_fused(case.params, 0)
+    oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
+    for f in (P.F_NU1, P.F_NU2):  # identical inputs on both sides (nu1 agrees to ~1e-15 only)
+        ctx.upload(f, oc.internal(f), oc.boundary(f))
+    for nuf, ff in ((False, P.FF_MUF), (True, P.FF_NUF)):
+        ctx.mixture_face_visc(case.params.mix, nuf)
+        ref = oc.mixture_face_visc(case.params.mix, nuf)
+        got = ctx.face_field(ff, m.nInternalFaces, m.nBoundaryFaces)
+        assert np.array_equal(got, ref)
+        assert np.isfinite(ref).all() and (ref > 0).all()
+    with pytest.raises(capi.SsamError):
+        ctx.face_field(7, 1, 1)
+
+
+def test_field_min_max(ctx):
+    """"Min/max T" of fluid/TEqn.H:42-43, plus odd sizes for the two-pass reduction"""
+    case = small_cases()["cfg1_sheared_graded"]()
+    ctx.load_case(case)
+    oc = oracle_case(case, apply_bc=False)
+    assert ctx.field_min_max(P.F_T) == O.field_min_max([oc], P.F_T)
+    rng = np.random.default_rng(17)
+    for dims in [(1, 1, 1), (7, 3, 1), (33, 9, 5), (64, 64, 20)]:
+        m = M.hex_block(*dims)
+        ctx.mesh_set(m)
+        v = rng.standard_normal(m.nCells + m.nBoundaryFaces) * 10.0 ** rng.integers(-5, 5)
+        ctx.upload(P.F_T, v[: m.nCells], v[m.nCells:])
+        assert ctx.field_min_max(P.F_T) == (v.min(), v.max())
+    with pytest.raises(capi.SsamError):
+        ctx.field_min_max(P.F_U)
+    with pytest.raises(capi.SsamError):
+        ctx.field_min_max(P.F_QFRIC)  # never set on this mesh

@@ -88,6 +88,9 @@ def test_driver_call_sequence_matches_oracle(tmp_path, name):
         assert "friction.correct() skipped" in r.stdout
     oc = oracle_sequence(case)
     assert res, "driver wrote no fields"
+    lo, hi = O.field_min_max([oc], P.F_T)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("Min/max T:")][-1]
+    assert tuple(float(v) for v in line.split(":")[1].split()) == (lo, hi)
     for f, got in res.items():
         check_field(P.FIELD_NAMES[f], got, oc.field(f), f in BIT_EXACT)
 

@@ -109,3 +109,31 @@ def test_decomposed_equals_serial():
                 continue
             s = slice(p.patchStart[q] - p.nInternalFaces, p.patchStart[q] - p.nInternalFaces + p.patchSize[q])
             assert np.isfinite(oc.boundary(P.F_CURVATURE)[s]).all()
+
+
+def test_muf_nuf_closed_form():
+    """muf()/nuf() (…Mixture.C:163-202) on a uniform mesh: face value = mean of the two cell values"""
+    from solidstateamfoam_b200 import cases
+
+    case = cases.cfg1(dims=(6, 5, 4))
+    m = case.mesh
+    oc = O.OracleCase(m)
+    rng = np.random.default_rng(2)
+    n = m.nCells + m.nBoundaryFaces
+    a, n1, n2 = rng.uniform(-0.2, 1.2, n), rng.uniform(1e-6, 1e3, n), np.full(n, 1.5e-5)
+    oc.set(P.F_ALPHA1, a[: m.nCells], a[m.nCells:])
+    oc.set(P.F_NU1, n1[: m.nCells], n1[m.nCells:])
+    oc.set(P.F_NU2, n2[: m.nCells], n2[m.nCells:])
+    mix = case.params.mix
+    muf, nuf = oc.mixture_face_visc(mix, False), oc.mixture_face_visc(mix, True)
+    nif = m.nInternalFaces
+    o, nb = m.owner[:nif], m.neighbour
+
+    def face(v):
+        return np.concatenate([0.5 * (v[o] + v[nb]), v[m.nCells:]])
+
+    la = np.clip(face(a), 0.0, 1.0)
+    mu_ref = la * mix.rho1 * face(n1) + (1 - la) * mix.rho2 * face(n2)
+    assert np.allclose(muf, mu_ref, rtol=1e-13)
+    assert np.allclose(nuf, mu_ref / (la * mix.rho1 + (1 - la) * mix.rho2), rtol=1e-13)
+    assert O.field_min_max([oc], P.F_NU1) == (n1.min(), n1.max())
