@@ -1,0 +1,121 @@
+"""ctypes wrapper of oracle/_ref/libssam_ref.so -- TEST INFRASTRUCTURE ONLY.
+
+The library is the reference's own model sources (viscoPlasticModels, frictionModels,
+incompressibleTwoPhaseThermalMixture), compiled unmodified from /root/reference against the stand-in OpenFOAM
+headers of oracle/ofstub/ (oracle/Makefile, target `ref`).  It exists only where the reference tree exists or
+where a prebuilt copy travelled with the repository snapshot; `available()` says which.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from solidstateamfoam_b200 import params as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "libssam_ref.so")
+REFERENCE_TREE = os.environ.get("SSAM_REFERENCE_TREE", "/root/reference")
+_lib = None
+
+
+def build() -> bool:
+    """(Re)build from the reference tree when it is present; keep a prebuilt library otherwise."""
+    if os.path.isdir(REFERENCE_TREE) and not os.environ.get("SSAM_REF_NOBUILD"):
+        r = subprocess.run(["make", "-C", _HERE, "ref", f"REF={REFERENCE_TREE}"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building oracle/_ref failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return os.path.exists(_SO)
+
+
+def available() -> bool:
+    try:
+        return build()
+    except RuntimeError:
+        return False
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not build():
+            raise RuntimeError("oracle/_ref/libssam_ref.so is absent and there is no reference tree to build it from")
+        L = C.CDLL(_SO)
+        vp, dp = C.c_void_p, C.POINTER(C.c_double)
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [C.POINTER(P.MeshDesc), C.POINTER(C.c_char_p), C.c_char_p]
+        L.ref_destroy.argtypes = [vp]
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_last_error.argtypes = [vp]
+        L.ref_info.restype = C.c_char_p
+        L.ref_info.argtypes = [vp]
+        L.ref_set_scalar.argtypes = [vp, C.c_char_p, dp, C.c_int]
+        L.ref_construct.argtypes = [vp, C.c_int]
+        L.ref_thermo_correct.argtypes = [vp]
+        L.ref_friction_correct.argtypes = [vp]
+        L.ref_eval.argtypes = [vp, C.c_char_p, dp]
+        L.ref_bc_rotational_slip.argtypes = [vp, C.c_char_p, dp]
+        _lib = L
+    return _lib
+
+
+class ReferenceError_(RuntimeError):
+    pass
+
+
+class ReferenceCase:
+    """The reference's mixture + friction model on one mesh, reading `<case_dir>/constant/{transport,friction}Properties`."""
+
+    def __init__(self, mesh, case_dir: str):
+        self.mesh = mesh
+        self._desc, self._keep = P.mesh_desc(mesh)
+        names = (C.c_char_p * mesh.nPatches)(*[n.encode() for n in mesh.patchName])
+        self.h = C.c_void_p(lib().ref_create(C.byref(self._desc), names, case_dir.encode()))
+        self.nTot = mesh.nCells + mesh.nBoundaryFaces
+
+    def close(self):
+        if self.h:
+            lib().ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st != 0:
+            raise ReferenceError_(lib().ref_last_error(self.h).decode())
+
+    def set(self, name: str, values, as_file: bool = False):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape == (self.nTot,), (name, v.shape)
+        self._chk(lib().ref_set_scalar(self.h, name.encode(), v.ctypes.data_as(C.POINTER(C.c_double)), 1 if as_file else 0))
+
+    def construct(self, with_friction: bool = True):
+        self._chk(lib().ref_construct(self.h, 1 if with_friction else 0))
+
+    def thermo_correct(self):
+        self._chk(lib().ref_thermo_correct(self.h))
+
+    def friction_correct(self):
+        self._chk(lib().ref_friction_correct(self.h))
+
+    def eval(self, what: str) -> np.ndarray:
+        n = self.mesh.nFaces if what in ("muf", "nuf") else self.nTot
+        out = np.zeros(n)
+        self._chk(lib().ref_eval(self.h, what.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def bc_rotational_slip(self, patch_name: str) -> np.ndarray:
+        """updateCoeffs() of the *RotationalSlip patch field described in <case_dir>/0/U -> U_b [n, 3]"""
+        p = self.mesh.patch_id(patch_name)
+        out = np.zeros((int(self.mesh.patchSize[p]), 3))
+        self._chk(lib().ref_bc_rotational_slip(self.h, patch_name.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def info(self) -> str:
+        return lib().ref_info(self.h).decode()

@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Freezes outputs of the reference's own model sources (oracle/_ref, see oracle/Makefile `ref`) into
+tests/golden/reference_sources.npz, so that tests/test_reference_golden.py can check the oracle against the
+reference on machines where /root/reference does not exist (the GPU box).
+
+Run where the reference tree is mounted:   python tests/golden/gen_reference_golden.py
+Every array is the reference's result for a deterministic synthetic case (solidstateamfoam_b200.cases, Philox
+seeds); `inputs_sha256` guards against the case generators drifting away from what was frozen."""
+import hashlib
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+import numpy as np
+
+from solidstateamfoam_b200 import cases
+
+SHEAR = (1.0, 0.3, 0.1, 0.0, 1.0, 0.2, 0.0, 0.0, 1.0)
+GOLDEN_CASES = {
+    "cfg1_sheppardwright_constantslip": lambda: cases.cfg1(dims=(7, 6, 5), affine=SHEAR, grading=(2.0, 0.5, 3.0)),
+    "cfg2_fks_cubic_kelvin": lambda: cases.cfg2(dims=(6, 6, 5)),
+    "cfg2_fks_cubic_celsius": lambda: cases.cfg2(dims=(5, 5, 4), units="Celsius"),
+    "cfg3_poly_exponentialslip": lambda: cases.cfg3(base=(4, 4, 4)),
+    "cfg4_nortonhoff": lambda: cases.cfg4(dims=(5, 5, 4)),
+}
+
+
+def inputs_digest(case) -> str:
+    h = hashlib.sha256()
+    m = case.mesh
+    for a in (m.owner, m.neighbour, m.Sf, m.weights, m.V, m.C, case.U_i, case.U_b, case.T_i, case.T_b, case.alpha1_i,
+              case.alpha1_b, case.p_i, case.p_b):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def main():
+    from ref_sequence import run_reference
+
+    out = {}
+    for name, mk in GOLDEN_CASES.items():
+        case = mk()
+        ref, _ = run_reference(case)
+        out[name + "/inputs_sha256"] = np.frombuffer(inputs_digest(case).encode(), dtype=np.uint8)
+        for k, v in ref.items():
+            out[name + "/" + k] = v
+        print(name, case.mesh.nCells, "cells,", len(ref), "fields")
+    path = os.path.join(HERE, "reference_sources.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -363,3 +363,36 @@ def test_field_min_max(ctx):
         ctx.field_min_max(P.F_U)
     with pytest.raises(capi.SsamError):
         ctx.field_min_max(P.F_QFRIC)  # never set on this mesh
+
+
+def test_gpu_against_frozen_reference_source_outputs(ctx):
+    """The CUDA path against outputs of the reference's OWN model sources (tests/golden/reference_sources.npz,
+    frozen from oracle/_ref by tests/golden/gen_reference_golden.py) -- no oracle in between; <= 1e-11 relative."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from gen_reference_golden import GOLDEN_CASES, inputs_digest
+
+    golden = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sources.npz"))
+    names = {"nu1": P.F_NU1, "nu2": P.F_NU2, "sigmaf": P.F_SIGMAF, "sigmay": P.F_SIGMAY, "nu": P.F_NU, "mu": P.F_MUEFF,
+             "rho": P.F_RHO, "cp": P.F_CP, "k": P.F_K, "qvisc": P.F_QVISC, "qfric": P.F_QFRIC}
+    checked = 0
+    for cname, mk in GOLDEN_CASES.items():
+        case = mk()
+        assert inputs_digest(case) == bytes(golden[cname + "/inputs_sha256"]).decode()
+        ctx.load_case(case)
+        ctx.update_fused(case.params, 0)
+        for key, f in names.items():
+            if cname + "/" + key not in golden.files:
+                continue
+            gi, gb = ctx.download(f)
+            check_field(f"{cname}/{key} vs reference sources", np.concatenate([gi, gb]), golden[cname + "/" + key],
+                        f in (P.F_RHO, P.F_CP, P.F_NU2))
+            checked += 1
+        for nuf, ff, key in ((False, P.FF_MUF, "muf"), (True, P.FF_NUF, "nuf")):
+            ctx.mixture_face_visc(case.params.mix, nuf)
+            got = ctx.face_field(ff, case.mesh.nInternalFaces, case.mesh.nBoundaryFaces)
+            check_field(f"{cname}/{key} vs reference sources", got, golden[cname + "/" + key], False)
+            checked += 1
+    assert checked >= 50

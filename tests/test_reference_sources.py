@@ -1,0 +1,123 @@
+"""The oracle against the reference's OWN model sources.
+
+oracle/_ref/libssam_ref.so is the reference's viscoPlasticModels, frictionModels and
+incompressibleTwoPhaseThermalMixture translation units, compiled unmodified from /root/reference against the
+stand-in OpenFOAM headers of oracle/ofstub/ (oracle/Makefile `ref`).  Both sides are CPU libm code evaluating
+the same expression trees on the same inputs, so every field must agree BIT FOR BIT -- any transcription error
+in oracle/oracle.cpp (operator order, max/min argument order, a field where a scalar belongs) shows up here.
+Skipped where neither the reference tree nor a prebuilt library exists; tests/test_reference_golden.py then
+still checks the oracle against the outputs frozen from this library.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from oracle import pyref as R
+from solidstateamfoam_b200 import cases
+from solidstateamfoam_b200 import params as P
+
+from ref_sequence import run_oracle, run_reference
+
+pytestmark = pytest.mark.skipif(not R.available(), reason="no reference tree and no prebuilt oracle/_ref")
+
+SHEAR = (1.0, 0.3, 0.1, 0.0, 1.0, 0.2, 0.0, 0.0, 1.0)
+CASES = {
+    "cfg1_sheppardwright_constantslip": lambda: cases.cfg1(dims=(9, 7, 6), affine=SHEAR, grading=(2.0, 0.5, 3.0)),
+    "cfg2_fks_cubic_kelvin": lambda: cases.cfg2(dims=(8, 7, 5)),
+    "cfg2_fks_cubic_celsius": lambda: cases.cfg2(dims=(6, 6, 4), units="Celsius"),
+    "cfg3_poly_exponentialslip": lambda: cases.cfg3(base=(6, 6, 6)),
+    "cfg4_nortonhoff": lambda: cases.cfg4(dims=(6, 5, 5)),
+}
+
+
+@pytest.mark.parametrize("form", [O.FAITHFUL, O.FUSED], ids=["faithful", "fused"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_equals_reference_sources_bit_for_bit(name, form, tmp_path):
+    case = CASES[name]()
+    ref, info = run_reference(case, str(tmp_path))
+    orc = run_oracle(case, form)
+    assert set(ref) == set(orc)
+    assert len(ref) >= 9
+    for k in ref:
+        same = (ref[k] == orc[k]) | (np.isnan(ref[k]) & np.isnan(orc[k]))
+        assert same.all(), f"{name}/{k}: {np.count_nonzero(~same)} of {same.size} values differ from the reference sources"
+    # the reference's own run-time selection and Info output
+    assert "Selecting incompressible transport model" in info
+    if "qfric" in ref:
+        assert "Selecting stick model" in info and "Center for patch zmax found to be at" in info
+        assert np.count_nonzero(ref["qfric"]) > 0
+
+
+@pytest.mark.parametrize("name", ["cfg1_sheppardwright_constantslip", "cfg3_poly_exponentialslip"])
+def test_rotational_slip_bc_equals_reference_sources(name, tmp_path):
+    """boundaryConditions/*RotationalSlip*::updateCoeffs() against the oracle's restatement: bit-exact U_b"""
+    case = CASES[name]()
+    d = str(tmp_path)
+    cases.write_case_dir(d, case)
+    rc = R.ReferenceCase(case.mesh, d)
+    ub_ref = rc.bc_rotational_slip("zmax")
+    oc = O.OracleCase(case.mesh, case.patch_u_bc)
+    oc.set(P.F_U, case.U_i, case.U_b)
+    oc.bc_rotational_slip(case.rotslip)
+    sl = case.mesh.patch_slice_b(case.mesh.patch_id("zmax"))
+    ub = oc.boundary(P.F_U)[sl]
+    assert ub_ref.shape == ub.shape and np.abs(ub_ref).max() > 0
+    assert np.array_equal(ub_ref, ub)
+
+
+def test_reference_extreme_inputs(tmp_path):
+    """limiters, alpha outside [0,1], temperatures outside [Ta,Tm] / [Tmin,Tmax], tiny and huge strain rates"""
+    case = cases.cfg2(dims=(6, 5, 4))
+    rng = np.random.default_rng(5)
+    n, nb = case.mesh.nCells, case.mesh.nBoundaryFaces
+    case.T_i = rng.choice([1.0, 150.0, 293.0, 500.0, 855.0, 2000.0], n)
+    case.T_b = rng.choice([1.0, 293.0, 700.0, 3000.0], nb)
+    case.alpha1_i = rng.choice([-0.3, 0.0, 1e-12, 0.5, 1.0, 1.7], n)
+    case.alpha1_b = rng.choice([-0.3, 0.0, 0.5, 1.0, 1.7], nb)
+    case.U_i = case.U_i * rng.choice([0.0, 1e-12, 1.0, 1e6], n)[:, None]
+    ref, _ = run_reference(case, str(tmp_path))
+    orc = run_oracle(case)
+    for k in ref:
+        same = (ref[k] == orc[k]) | (np.isnan(ref[k]) & np.isnan(orc[k]))
+        assert same.all(), k
+
+
+def _break(tmp_path, case, fname, old, new):
+    d = str(tmp_path)
+    cases.write_case_dir(d, case)
+    p = os.path.join(d, "constant", fname)
+    txt = open(p).read()
+    assert old in txt
+    open(p, "w").write(txt.replace(old, new))
+    m = case.mesh
+    n = m.nCells + m.nBoundaryFaces
+    rc = R.ReferenceCase(m, d)
+    rc.set("temp", np.full(n, 500.0))
+    rc.set("epsilonDotEq", np.ones(n))
+    rc.set("muEff", np.ones(n))
+    rc.set("p", np.ones(n))
+    rc.set("__magSymmGradU", np.ones(n))
+    rc.set("alpha.metal", np.ones(n), as_file=True)
+    rc.set("qfric", np.zeros(n), as_file=True)
+    return rc
+
+
+def test_reference_error_messages_match_the_host_mirror(tmp_path):
+    """the messages solidstateamfoam_b200/host reproduces are the reference's own (stickModelNew.C, ...Mixture.C)"""
+    case = cases.cfg2(dims=(3, 3, 3))
+    rc = _break(tmp_path / "a", case, "frictionProperties", "stickModel constantSlipStick;", "stickModel stickySlip;")
+    with pytest.raises(R.ReferenceError_) as e:
+        rc.construct()
+    assert "Unknown stickModel type stickySlip" in str(e.value)
+    assert "constantSlipStick exponentialSlipStick" in str(e.value)
+    rc = _break(tmp_path / "b", case, "transportProperties", "units Kelvin;", "units Rankine;")
+    rc.construct()
+    with pytest.raises(R.ReferenceError_) as e:
+        rc.eval("k")
+    assert "Unknown conductivity function units Rankine for phase 1" in str(e.value)
+    rc = _break(tmp_path / "c", case, "transportProperties", "        a1 ", "        a1missing ")
+    with pytest.raises(R.ReferenceError_) as e:
+        rc.construct()
+    assert "keyword a1 is undefined in dictionary" in str(e.value)
