@@ -5,13 +5,22 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library; the product (solidstateamfoam_b200/) never does.
 //
-// PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, fixtures or example cases
-//  and cannot be compiled here (it needs OpenFOAM v1806, absent offline,
-// SURVEY.md §8c).  This file is therefore a *restatement*: the closed-form expressions follow
+// PARITY PARTLY PINNED.  The reference ships no tests, fixtures or example cases and the solver
+// cannot be built here (it needs OpenFOAM v1806, absent offline).  Two tiers therefore:
+//  * PINNED against the reference's own source text: the closed-form model expressions -- SheppardWright, FKS,
+//    NortonHoff, the mixture's mu/nu/k/cp/rho/muf/nuf, constant/exponentialSlipStick qvisc/qfric, both
+//    rotational-slip boundary conditions.  Their translation units are compiled UNMODIFIED from /root/reference
+//    against stand-in OpenFOAM headers (oracle/ofstub, oracle/Makefile target `ref` -> oracle/_ref) and this file
+//    must match them bit for bit (tests/test_reference_sources.py; outputs frozen in tests/golden/
+//    reference_sources.npz for machines without the reference tree).
+//  * PARITY UNPINNED: everything that is OpenFOAM library behaviour rather than reference source -- the
+//    Gauss-linear gradient, face interpolation, boundary/processor-patch evaluation, field-algebra semantics
+//    (also assumed by the stand-in headers), interfaceProperties::calculateK, and fluid/calculateStrain.H.
+//    These are restatements: the closed-form expressions follow
 // the cited reference lines operator by operator (C++ left-to-right association, one rounded
 // FP64 operation per operator, no FMA: build with -ffp-contract=off), and the OpenFOAM
 // semantics it relies on (Gauss-linear gradient, symm/mag, max/min argument order, boundary
-// evaluation) are restated from OpenFOAM v1806 as described in SURVEY.md Appendix B.  It is
+// evaluation) are restated from OpenFOAM v1806 as described in SURVEY.md Appendix B.  They are
 // pinned instead by (1) mpmath >=50-digit known-answer vectors (tests/golden), (2) analytic
 // gradient cases, (3) two independent forms agreeing bit for bit:
 //   form 0 "faithful": field-at-a-time, one loop + one temporary per operator over internal

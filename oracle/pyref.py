@@ -57,6 +57,7 @@ def lib():
         L.ref_friction_correct.argtypes = [vp]
         L.ref_eval.argtypes = [vp, C.c_char_p, dp]
         L.ref_bc_rotational_slip.argtypes = [vp, C.c_char_p, dp]
+        L.ref_calculate_strain.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -116,6 +117,19 @@ class ReferenceCase:
         out = np.zeros((int(self.mesh.patchSize[p]), 3))
         self._chk(lib().ref_bc_rotational_slip(self.h, patch_name.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def calculate_strain(self, deltaT: float, gradU, p_rgh, epsilonEq):
+        """fluid/calculateStrain.H verbatim (its fvm solve is a no-op) -> dict(Z, sigmaf, epsilonEq, sigmavm)"""
+        dp = C.POINTER(C.c_double)
+        g = np.ascontiguousarray(gradU, dtype=np.float64).reshape(-1)
+        assert g.size == 9 * self.nTot
+        pr = np.ascontiguousarray(p_rgh, dtype=np.float64)
+        eq = np.array(epsilonEq, dtype=np.float64)
+        Z, sf, vm = np.zeros(self.nTot), np.zeros(self.nTot), np.zeros(self.nTot)
+        self._chk(lib().ref_calculate_strain(self.h, deltaT, g.ctypes.data_as(dp), pr.ctypes.data_as(dp),
+                                             eq.ctypes.data_as(dp), Z.ctypes.data_as(dp), sf.ctypes.data_as(dp),
+                                             vm.ctypes.data_as(dp)))
+        return {"Z": Z, "sigmaf": sf, "epsilonEq": eq, "sigmavm": vm}
 
     def info(self) -> str:
         return lib().ref_info(self.h).decode()

@@ -239,4 +239,38 @@ int ref_bc_rotational_slip(ref_case* h, const char* patchName, double* out) {
     });
 }
 
+// fluid/calculateStrain.H, included verbatim with the solver's variable names in scope.  Its fvm:: transport solve
+// of epsilonEq is a no-op here (ofstub.H), as it is outside ssam_stress_strain.  gradU: [9*nTot] from the oracle.
+int ref_calculate_strain(ref_case* h, double deltaT, const double* gradUIn, const double* pRgh, double* epsilonEqInOut,
+                         double* ZOut, double* sigmafOut, double* sigmavmOut) {
+    RefCase* c = RC(h);
+    return guarded(c, [&]() {
+        fvMesh& mesh = c->mesh;
+        const size_t n = size_t(c->nTot);
+        mesh.gradUValues.resize(n);
+        for (size_t i = 0; i < n; ++i)
+            for (int k = 0; k < 9; ++k) mesh.gradUValues[i].c[k] = gradUIn[9 * i + k];
+        mesh.runTime.deltaTValue = deltaT;
+        Time& runTime = mesh.runTime;
+        incompressibleTwoPhaseThermalMixture& thermo = *c->thermo;
+        const volVectorField& U = *c->U;
+        const volScalarField& epsilonDotEq = mesh.lookupObject<volScalarField>("epsilonDotEq");
+        const volScalarField& temp = mesh.lookupObject<volScalarField>("temp");
+        const volScalarField& muEff = mesh.lookupObject<volScalarField>("muEff");
+        volScalarField Z(mesh, "Z"), sigmaf(mesh, "sigmafPP"), sigmavm(mesh, "sigmavm"), epsilonEq(mesh, "epsilonEq"),
+            p_rgh(mesh, "p_rgh"), rho(mesh, "rho");
+        surfaceScalarField rhoPhi(mesh, "rhoPhi");
+        dimensionedScalar gammaEpsilon("gammaEpsilon", dimless, 0.0);
+        const bool finalIter = true;
+        p_rgh.values().assign(pRgh, pRgh + n);
+        epsilonEq.values().assign(epsilonEqInOut, epsilonEqInOut + n);
+        (void)runTime; (void)U; (void)finalIter;
+#include "calculateStrain.H"
+        std::memcpy(epsilonEqInOut, epsilonEq.values().data(), n * sizeof(double));
+        std::memcpy(ZOut, Z.values().data(), n * sizeof(double));
+        std::memcpy(sigmafOut, sigmaf.values().data(), n * sizeof(double));
+        std::memcpy(sigmavmOut, sigmavm.values().data(), n * sizeof(double));
+    });
+}
+
 }  // extern "C"

@@ -101,6 +101,17 @@ def build_oracle(force: bool = False, verbose: bool = False) -> str:
     return os.path.join(odir, "liboracle.so")
 
 
+def build_oracle_ref(verbose: bool = False) -> str | None:
+    """oracle/_ref/libssam_ref.so: the reference's own model sources against oracle/ofstub (test infrastructure).
+    Built only where the reference tree is mounted; elsewhere a prebuilt copy (it travels with the snapshot) is kept."""
+    odir = os.path.join(ROOT, "oracle")
+    ref = os.environ.get("SSAM_REFERENCE_TREE", "/root/reference")
+    so = os.path.join(odir, "_ref", "libssam_ref.so")
+    if os.path.isdir(ref):
+        _run(["make", "-C", odir, "ref", f"REF={ref}"], verbose)
+    return so if os.path.exists(so) else None
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_meshgen(force, verbose)
     build_cuda(force, verbose)

@@ -37,12 +37,20 @@ def inputs_digest(case) -> str:
 
 
 def main():
+    import tempfile
+
+    from oracle import pyref as R
     from ref_sequence import run_reference
 
     out = {}
     for name, mk in GOLDEN_CASES.items():
         case = mk()
-        ref, _ = run_reference(case)
+        d = tempfile.mkdtemp(prefix="ssam_golden_")
+        ref, _ = run_reference(case, d)
+        if case.rotslip is not None:  # boundaryConditions/*RotationalSlip*::updateCoeffs()
+            rc = R.ReferenceCase(case.mesh, d)
+            ref["bc_Ub"] = rc.bc_rotational_slip("zmax").reshape(-1)
+            rc.close()
         out[name + "/inputs_sha256"] = np.frombuffer(inputs_digest(case).encode(), dtype=np.uint8)
         for k, v in ref.items():
             out[name + "/" + k] = v

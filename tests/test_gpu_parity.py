@@ -382,6 +382,12 @@ def test_gpu_against_frozen_reference_source_outputs(ctx):
         case = mk()
         assert inputs_digest(case) == bytes(golden[cname + "/inputs_sha256"]).decode()
         ctx.load_case(case)
+        if cname + "/bc_Ub" in golden.files:  # *RotationalSlip*::updateCoeffs() of the reference itself
+            _, ub = ctx.download(P.F_U)
+            sl = case.mesh.patch_slice_b(case.mesh.patch_id("zmax"))
+            check_field(f"{cname}/U_b vs reference sources", ub[sl].reshape(-1), golden[cname + "/bc_Ub"],
+                        case.rotslip.model == P.ROTSLIP_CONSTANT)
+            checked += 1
         ctx.update_fused(case.params, 0)
         for key, f in names.items():
             if cname + "/" + key not in golden.files:

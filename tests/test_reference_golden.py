@@ -24,6 +24,13 @@ def test_oracle_reproduces_frozen_reference_outputs(name, form):
     assert inputs_digest(case) == bytes(GOLDEN[name + "/inputs_sha256"]).decode(), \
         "the synthetic case changed: regenerate tests/golden/reference_sources.npz"
     orc = run_oracle(case, form)
+    if case.rotslip is not None:
+        from solidstateamfoam_b200 import params as P
+
+        oc = O.OracleCase(case.mesh, case.patch_u_bc)
+        oc.set(P.F_U, case.U_i, case.U_b)
+        oc.bc_rotational_slip(case.rotslip)
+        orc["bc_Ub"] = oc.boundary(P.F_U)[case.mesh.patch_slice_b(case.mesh.patch_id("zmax"))].reshape(-1)
     keys = [k.split("/", 1)[1] for k in GOLDEN.files if k.startswith(name + "/") and not k.endswith("inputs_sha256")]
     assert sorted(keys) == sorted(orc)
     for k in keys:

@@ -67,6 +67,61 @@ def test_rotational_slip_bc_equals_reference_sources(name, tmp_path):
     assert np.array_equal(ub_ref, ub)
 
 
+def _flatten_coeffs(path, name):
+    """calculateStrain.H looks Q, R, sigmaR, A, n up in the phase dictionary itself (:6-10): move the entries of
+    the optional <model>Coeffs sub-dictionary one level up, which the models accept too (optionalSubDict)."""
+    txt = open(path).read()
+    i = txt.index(name)
+    j = txt.index("{", i)
+    depth, k = 1, j + 1
+    while depth:
+        depth += {"{": 1, "}": -1}.get(txt[k], 0)
+        k += 1
+    open(path, "w").write(txt[:i] + txt[j + 1:k - 1] + txt[k:])
+
+
+def test_calculate_strain_fragment_equals_oracle(tmp_path):
+    """fluid/calculateStrain.H included verbatim (transport solve stubbed out) against oracle stress_strain: bit-exact"""
+    case = CASES["cfg1_sheppardwright_constantslip"]()
+    d = str(tmp_path)
+    cases.write_case_dir(d, case)
+    _flatten_coeffs(os.path.join(d, "constant", "transportProperties"), "SheppardWrightCoeffs")
+    m = case.mesh
+    n, nb = m.nCells, m.nBoundaryFaces
+    rng = np.random.default_rng(9)
+    prgh = 1e5 * (1.0 + 0.05 * rng.standard_normal(n + nb))
+    mu = 10.0 ** rng.uniform(2, 7, n + nb)
+    oc = O.OracleCase(m, case.patch_u_bc)
+    oc.set(P.F_U, case.U_i, case.U_b)
+    oc.bc_rotational_slip(case.rotslip)
+    oc.set(P.F_T, case.T_i, case.T_b)
+    oc.strain_rate(float(np.sqrt(2.0 / 3.0)), P.F_EPSDOT)
+    oc.set(P.F_MUEFF, mu[:n], mu[n:])
+    oc.set(P.F_PRGH, prgh[:n], prgh[n:])
+    v = case.params.visc1
+    prm = P.StressStrainParams(Q=v.Q, R=v.R, sigmaR=v.sigmaR, A=v.A, n=v.n, deltaT=2.5e-4)
+    rc = R.ReferenceCase(m, d)
+    cat = np.concatenate
+    rc.set("temp", cat([case.T_i, case.T_b]))
+    rc.set("epsilonDotEq", oc.field(P.F_EPSDOT).copy())
+    rc.set("muEff", mu)
+    rc.set("p", cat([case.p_i, case.p_b]))
+    rc.set("__magSymmGradU", np.ones(n + nb))
+    rc.set("alpha.metal", cat([case.alpha1_i, case.alpha1_b]), as_file=True)
+    rc.set("qfric", np.zeros(n + nb), as_file=True)
+    rc.construct(with_friction=False)
+    eq = np.zeros(n + nb)
+    for step in range(2):  # the second pass accumulates epsilonEq
+        oc.stress_strain(prm)
+        ref = rc.calculate_strain(prm.deltaT, oc.field(P.F_GRADU), prgh, eq)
+        eq = ref["epsilonEq"]
+        for key, f in (("Z", P.F_Z), ("sigmaf", P.F_SIGMAF_PP), ("epsilonEq", P.F_EPSEQ), ("sigmavm", P.F_SIGMAVM)):
+            assert np.array_equal(ref[key], oc.field(f)), (step, key)
+        if step == 0:
+            assert np.array_equal(ref["epsilonEq"], oc.field(P.F_DEPSEQ))  # 0 + dEpsilonEq
+    assert "Max. von Mises stress" in rc.info()
+
+
 def test_reference_extreme_inputs(tmp_path):
     """limiters, alpha outside [0,1], temperatures outside [Ta,Tm] / [Tmin,Tmax], tiny and huge strain rates"""
     case = cases.cfg2(dims=(6, 5, 4))
