@@ -198,6 +198,19 @@ SSAM_API int64_t ssam_launch_count(const ssam_ctx* ctx);
 /* Fused cell-kernel variant: 1 (default) = tiled, inputs of 256 consecutive cells staged in shared memory
  * by 1-D bulk async copies; 0 = one thread per cell with direct global loads.  Results are identical. */
 SSAM_API ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant);
+/* Cell layout of the device planes, to be chosen before ssam_mesh_set:
+ *   SSAM_LAYOUT_CALLER  (0) the caller's cell numbering;
+ *   SSAM_LAYOUT_AUTO    (1, default) tile-compact when it removes at least one out-of-tile neighbour per cell;
+ *   SSAM_LAYOUT_COMPACT (2) always tile-compact.
+ * Tile-compact: runs of 64 consecutive cells are regrouped so that 256 consecutive device cells form a compact
+ * brick of the mesh.  ssam_field_upload/download and ssam_update_fused_host apply the permutation, every
+ * addressing table above stays in the caller's numbering, per-cell face order (and so every result bit) is
+ * unchanged; only ssam_field_device_ptr exposes the device order (SSAM_ADDR_CELL_ORDER tells which cell is where).
+ * The chunk-pipelined ssam_update_fused_host needs SSAM_LAYOUT_CALLER (it falls back to unpipelined otherwise). */
+enum { SSAM_LAYOUT_CALLER = 0, SSAM_LAYOUT_AUTO = 1, SSAM_LAYOUT_COMPACT = 2 };
+SSAM_API ssam_status ssam_set_cell_layout(ssam_ctx* ctx, int mode);
+/* 1 when the current mesh is held in tile-compact order */
+SSAM_API int ssam_cell_layout_is_compact(const ssam_ctx* ctx);
 /* Per-kernel timing for the roofline figure: when enabled, every fused update brackets its cell
  * kernel (the dominant kernel) with CUDA events on the launching stream.  ssam_profile_get
  * synchronises, returns the summed cell-kernel milliseconds and the number of launches since the
@@ -224,7 +237,9 @@ enum {
     SSAM_ADDR_HALO_PATCH_OFFSETS = 7, /* [nProcPatches+1] offsets of each processor patch in the send list   */
     SSAM_ADDR_FRIC_CELLS = 8,   /* [patchSize] faceCells of the last friction patch used                     */
     SSAM_ADDR_FACE_COLOUR = 9,  /* [nInternalFaces] greedy face colouring (scatter variant)                  */
-    SSAM_ADDR_COUNT = 10
+    SSAM_ADDR_CELL_ORDER = 10,  /* [nCells] caller's cell label held at each position of the device planes
+                                   (identity unless the tile-compact layout is active, see ssam_set_cell_layout) */
+    SSAM_ADDR_COUNT = 11
 };
 SSAM_API ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n);
 SSAM_API ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t n);

@@ -18,7 +18,7 @@ _lib = None
 # every exported symbol of include/ssam_gpu.h (checked by tests/test_abi_symbols.py)
 SYMBOLS = [
     "ssam_create", "ssam_destroy", "ssam_last_error", "ssam_sync", "ssam_set_stream", "ssam_set_blocking",
-    "ssam_abi_version", "ssam_launch_count", "ssam_set_cell_kernel", "ssam_profile_enable", "ssam_profile_get", "ssam_mesh_set", "ssam_patch_u_bc_set", "ssam_addressing_size",
+    "ssam_abi_version", "ssam_launch_count", "ssam_set_cell_kernel", "ssam_set_cell_layout", "ssam_cell_layout_is_compact", "ssam_profile_enable", "ssam_profile_get", "ssam_mesh_set", "ssam_patch_u_bc_set", "ssam_addressing_size",
     "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
@@ -62,6 +62,8 @@ def load():
     L.ssam_launch_count.restype = C.c_int64
     L.ssam_launch_count.argtypes = [vp]
     L.ssam_set_cell_kernel.argtypes = [vp, C.c_int]
+    L.ssam_set_cell_layout.argtypes = [vp, C.c_int]
+    L.ssam_cell_layout_is_compact.argtypes = [vp]
     L.ssam_profile_enable.argtypes = [vp, C.c_int]
     L.ssam_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.ssam_mesh_set.argtypes = [vp, C.POINTER(P.MeshDesc)]
@@ -168,6 +170,13 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.L.ssam_launch_count(self.h))
+
+    def set_cell_layout(self, mode: int):
+        """0 = caller's cell order, 1 = tile-compact when it pays (default), 2 = always; before mesh_set"""
+        self._chk(self.L.ssam_set_cell_layout(self.h, mode))
+
+    def layout_is_compact(self) -> bool:
+        return bool(self.L.ssam_cell_layout_is_compact(self.h))
 
     def set_cell_kernel(self, variant: int):
         self._chk(self.L.ssam_set_cell_kernel(self.h, variant))

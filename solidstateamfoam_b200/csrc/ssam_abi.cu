@@ -46,6 +46,14 @@ struct ssam_ctx {
     int hostChunks = -1;  // >= 0 overrides the chunk count of the host-staged pipeline (0/1 = unpipelined)
     int nTilesOversize = 0;
     int cellKernel = 1;  // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged
+    // cell layout: 0 = the caller's numbering, 1 = tile-compact when it pays (default), 2 = always tile-compact
+    int layoutMode = 1;
+    int* perm = nullptr;      // device position i holds the caller's cell perm[i] (nullptr = identity)
+    int* faceKey = nullptr;   // internal faces: index of the face in the caller's mesh (permuted layout only)
+    std::vector<int> permHost;
+    int *origOwner = nullptr, *origNeighbour = nullptr;  // the caller's owner / neighbour (permuted layout only)
+    ssam_ctx* refAddr = nullptr;  // addressing tables in the caller's numbering, built on demand
+    double remotePerCellCaller = 0.0, remotePerCellCompact = 0.0;
     double *V = nullptr, *magSf_b = nullptr, *deltaCoeffs_b = nullptr;
     double* Cpl[3] = {nullptr, nullptr, nullptr};  // cell centres, then boundary-face centres
     unsigned char* bndFlags = nullptr;
@@ -179,6 +187,11 @@ ssam_status ensureFaceField(ssam_ctx* ctx, int ff) {
 }
 
 void freeMesh(ssam_ctx* c) {
+    if (c->refAddr) {
+        freeMesh(c->refAddr);
+        delete c->refAddr;
+        c->refAddr = nullptr;
+    }
     devFree(c->geo);
     devFree(c->owner);
     devFree(c->neighbour);
@@ -188,6 +201,11 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->tileDesc);
     devFree(c->tileIota);
     devFree(c->tileOrder);
+    devFree(c->perm);
+    devFree(c->faceKey);
+    devFree(c->origOwner);
+    devFree(c->origNeighbour);
+    c->permHost.clear();
     devFree(c->tileListInterior);
     devFree(c->tileListCoupled);
     devFree(c->V);
@@ -272,7 +290,7 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
     TRY(devAlloc(ctx, &cursor, size_t(nc) + 1));
     CU(cudaMemcpyAsync(cursor, ctx->extraStart, (size_t(nc) + 1) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     LAUNCH(k_extra_fill, gridFor(nF, 256), 256, ctx->owner, ctx->neighbour, ctx->bndFlags, nIF, nF, cursor, ctx->extra);
-    LAUNCH(k_extra_sort, gridFor(nc, 256), 256, ctx->extraStart, nc, ctx->extra);
+    LAUNCH(k_extra_sort, gridFor(nc, 256), 256, ctx->extraStart, nc, ctx->extra, ctx->faceKey, nIF);
     {
         int* bw = nullptr;
         TRY(devAlloc(ctx, &bw, 1));
@@ -325,7 +343,8 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
 
 ssam_status uploadAoS(ssam_ctx* ctx, const double* host, int n, int nc, double* const* planes, int offset) {
     if (n == 0) return SSAM_OK;
-    if (nc == 1) {
+    const int* perm = (offset == 0 && n == ctx->nCells) ? ctx->perm : nullptr;  // cell part in the library's order
+    if (nc == 1 && !perm) {
         CU(cudaMemcpyAsync(planes[0] + offset, host, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         return SSAM_OK;
     }
@@ -333,20 +352,21 @@ ssam_status uploadAoS(ssam_ctx* ctx, const double* host, int n, int nc, double* 
     CU(cudaMemcpyAsync(ctx->stage, host, size_t(n) * nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     PlanePtrs pl;
     for (int k = 0; k < 16; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
-    LAUNCH(k_aos_to_soa_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset);
+    LAUNCH(k_aos_to_soa_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset, perm);
     return SSAM_OK;
 }
 
 ssam_status downloadAoS(ssam_ctx* ctx, double* host, int n, int nc, double* const* planes, int offset) {
     if (n == 0) return SSAM_OK;
-    if (nc == 1) {
+    const int* perm = (offset == 0 && n == ctx->nCells) ? ctx->perm : nullptr;
+    if (nc == 1 && !perm) {
         CU(cudaMemcpyAsync(host, planes[0] + offset, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         return SSAM_OK;
     }
     TRY(ensureStage(ctx, size_t(n) * nc));
     PlanePtrs pl;
     for (int k = 0; k < 16; ++k) pl.p[k] = k < nc ? planes[k] : nullptr;
-    LAUNCH(k_soa_to_aos_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset);
+    LAUNCH(k_soa_to_aos_n, gridFor((long long)n * nc, 256), 256, ctx->stage, n, nc, pl, offset, perm);
     CU(cudaMemcpyAsync(host, ctx->stage, size_t(n) * nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     // the staging buffer is reused by the next transfer
     CU(cudaStreamSynchronize(ctx->stream));
@@ -683,6 +703,140 @@ ssam_status buildTileOrder(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     return SSAM_OK;
 }
 
+// ---- tile-compact cell layout ---------------------------------------------------------------------------------
+// The tiled kernel finds a face neighbour in shared memory only when it lies in the same 256 consecutive cells.
+// In blockMesh order such a tile is one x-row and 4 of a cell's 6 neighbours are elsewhere.  The library may
+// therefore keep the cells in its own order: runs of RUN consecutive caller cells are clustered greedily into
+// tiles of TILE/RUN runs that are mesh neighbours of each other (heaviest connection first; ties: the run
+// adjacent to the oldest member, then the lowest label) -- on a blockMesh box 64x2x2 bricks, 2 remote neighbours
+// per cell.  Runs stay contiguous, so uploads and downloads (which apply the permutation) remain coalesced.
+// Faces keep the caller's owner/neighbour roles and every cell still visits its faces in the caller's ascending
+// face order (k_extra_sort's key), so all results are bit-identical to the caller-order layout.
+constexpr int RUN = 64, RUNS_PER_TILE = TILE / RUN;
+
+struct PermutedMesh {
+    std::vector<int> perm, inv, owner, neighbour, faceKey;
+    std::vector<double> Sf, w, V, C;
+};
+
+// -> perm (library position -> caller cell); returns false when clustering does not pay
+bool computeCompactOrder(ssam_ctx* ctx, const ssam_mesh_desc* m, std::vector<int>& perm) {
+    const int nC = m->nCells, nIF = m->nInternalFaces;
+    const int nB = (nC + RUN - 1) / RUN;
+    std::vector<std::vector<int>> nb(nB);
+    long long remoteCaller = 0;
+    for (int f = 0; f < nIF; ++f) {
+        const int o = m->owner[f], n = m->neighbour[f];
+        if (o / TILE != n / TILE) remoteCaller += 2;
+        const int bo = o / RUN, bn = n / RUN;
+        if (bo == bn) continue;
+        nb[bo].push_back(bn);
+        nb[bn].push_back(bo);
+    }
+    std::vector<int> adjStart(nB + 1, 0), adjTo, adjW;
+    for (int b = 0; b < nB; ++b) {
+        std::vector<int>& v = nb[b];
+        std::sort(v.begin(), v.end());
+        for (size_t i = 0; i < v.size();) {
+            size_t j = i;
+            while (j < v.size() && v[j] == v[i]) ++j;
+            adjTo.push_back(v[i]);
+            adjW.push_back(int(j - i));
+            i = j;
+        }
+        adjStart[b + 1] = int(adjTo.size());
+        std::vector<int>().swap(v);
+    }
+    std::vector<char> assigned(nB, 0);
+    std::vector<int> full, partial;  // runs of complete tiles first, leftovers last (keeps tiles aligned)
+    struct Cand { int run, w, age; };
+    std::vector<Cand> cand;
+    for (int seed = 0; seed < nB; ++seed) {
+        if (assigned[seed]) continue;
+        int members[RUNS_PER_TILE];
+        int nMem = 0;
+        cand.clear();
+        auto add = [&](int b) {
+            assigned[b] = 1;
+            members[nMem++] = b;
+            for (int k = adjStart[b]; k < adjStart[b + 1]; ++k) {
+                const int j = adjTo[k];
+                if (assigned[j]) continue;
+                bool found = false;
+                for (Cand& q : cand)
+                    if (q.run == j) {
+                        q.w += adjW[k];
+                        found = true;
+                        break;
+                    }
+                if (!found) cand.push_back({j, adjW[k], nMem});
+            }
+        };
+        add(seed);
+        while (nMem < RUNS_PER_TILE && !cand.empty()) {
+            size_t best = 0;
+            for (size_t q = 1; q < cand.size(); ++q) {
+                const Cand &x = cand[q], &y = cand[best];
+                if (x.w > y.w || (x.w == y.w && (x.age < y.age || (x.age == y.age && x.run < y.run)))) best = q;
+            }
+            const int j = cand[best].run;
+            cand.erase(cand.begin() + long(best));
+            // the last (short) run of the mesh would misalign every later tile: it goes to the leftovers
+            if ((j + 1) * RUN > nC) continue;
+            add(j);
+        }
+        std::sort(members, members + nMem);
+        const bool whole = nMem == RUNS_PER_TILE && (members[nMem - 1] + 1) * RUN <= nC;
+        for (int k = 0; k < nMem; ++k) (whole ? full : partial).push_back(members[k]);
+    }
+    std::sort(partial.begin(), partial.end());
+    perm.clear();
+    perm.reserve(size_t(nC));
+    for (const std::vector<int>* lst : {&full, &partial})
+        for (int b : *lst)
+            for (int c = b * RUN; c < std::min(nC, (b + 1) * RUN); ++c) perm.push_back(c);
+    if (int(perm.size()) != nC) return false;  // (cannot happen; keeps a wrong layout from ever being used)
+    std::vector<int> inv(static_cast<size_t>(nC), 0);
+    for (int i = 0; i < nC; ++i) inv[size_t(perm[size_t(i)])] = i;
+    long long remoteCompact = 0;
+    for (int f = 0; f < nIF; ++f)
+        if (inv[size_t(m->owner[f])] / TILE != inv[size_t(m->neighbour[f])] / TILE) remoteCompact += 2;
+    ctx->remotePerCellCaller = double(remoteCaller) / nC;
+    ctx->remotePerCellCompact = double(remoteCompact) / nC;
+    // pays when at least one gather per cell moves from global memory into the tile
+    return ctx->layoutMode == 2 || ctx->remotePerCellCaller - ctx->remotePerCellCompact >= 1.0;
+}
+
+void permuteMesh(const ssam_mesh_desc* m, PermutedMesh& pm) {
+    const int nC = m->nCells, nIF = m->nInternalFaces, nF = m->nFaces;
+    pm.inv.assign(size_t(nC), 0);
+    for (int i = 0; i < nC; ++i) pm.inv[size_t(pm.perm[size_t(i)])] = i;
+    // internal faces: stable counting sort by the new label of the (unchanged) owner
+    std::vector<int> start(size_t(nC) + 1, 0);
+    for (int f = 0; f < nIF; ++f) ++start[size_t(pm.inv[size_t(m->owner[f])]) + 1];
+    for (int c = 0; c < nC; ++c) start[size_t(c) + 1] += start[size_t(c)];
+    pm.faceKey.assign(size_t(nIF), 0);
+    for (int f = 0; f < nIF; ++f) pm.faceKey[size_t(start[size_t(pm.inv[size_t(m->owner[f])])]++)] = f;
+    pm.owner.resize(size_t(nF));
+    pm.neighbour.resize(size_t(nIF));
+    pm.Sf.resize(size_t(nF) * 3);
+    pm.w.resize(size_t(nF));
+    for (int g = 0; g < nF; ++g) {
+        const int f = g < nIF ? pm.faceKey[size_t(g)] : g;
+        pm.owner[size_t(g)] = pm.inv[size_t(m->owner[f])];
+        if (g < nIF) pm.neighbour[size_t(g)] = pm.inv[size_t(m->neighbour[f])];
+        for (int k = 0; k < 3; ++k) pm.Sf[size_t(g) * 3 + k] = m->Sf[size_t(f) * 3 + k];
+        pm.w[size_t(g)] = m->weights[f];
+    }
+    pm.V.resize(size_t(nC));
+    pm.C.resize(size_t(nC) * 3);
+    for (int i = 0; i < nC; ++i) {
+        const int c = pm.perm[size_t(i)];
+        pm.V[size_t(i)] = m->V[c];
+        for (int k = 0; k < 3; ++k) pm.C[size_t(i) * 3 + k] = m->C[size_t(c) * 3 + k];
+    }
+}
+
 ssam_status mixtureCalcNu(ssam_ctx* ctx, const ssam_mixture_params* p) {
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(need(ctx, SSAM_F_NU1, "nu1"));
@@ -715,6 +869,7 @@ ssam_status ssam_create(ssam_ctx** out, int device) {
     CU(cudaSetDevice(device));
     ssam_ctx* c = new ssam_ctx;
     c->device = device;
+    if (const char* lm = std::getenv("SSAM_LAYOUT")) c->layoutMode = std::max(0, std::min(2, std::atoi(lm)));
     if (cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return fail(nullptr, SSAM_ERR_CUDA, "cudaStreamCreate failed");
@@ -778,6 +933,14 @@ ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant) {
     return SSAM_OK;
 }
 
+ssam_status ssam_set_cell_layout(ssam_ctx* ctx, int mode) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CHECK(mode >= SSAM_LAYOUT_CALLER && mode <= SSAM_LAYOUT_COMPACT, SSAM_ERR_INVALID, "bad cell layout mode");
+    ctx->layoutMode = mode;
+    return SSAM_OK;
+}
+int ssam_cell_layout_is_compact(const ssam_ctx* ctx) { return (ctx && ctx->perm) ? 1 : 0; }
+
 ssam_status ssam_profile_enable(ssam_ctx* ctx, int enable) {
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     ctx->profile = enable != 0;
@@ -812,6 +975,32 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
           SSAM_ERR_INVALID, "null mesh array");
     CU(cudaStreamSynchronize(ctx->stream));
     freeMesh(ctx);
+    // tile-compact layout: permute the mesh on the host, then build everything from the permuted arrays
+    PermutedMesh pm;
+    ssam_mesh_desc mm;
+    const ssam_mesh_desc* callerMesh = m;
+    bool permuted = false;
+    if (ctx->layoutMode != SSAM_LAYOUT_CALLER && m->nCells >= 2 * TILE && m->nInternalFaces > 0 && m->neighbour) {
+        for (int f = 1; f < m->nInternalFaces; ++f)
+            CHECK(m->owner[f] >= m->owner[f - 1], SSAM_ERR_INVALID,
+                  "owner[] of the internal faces is not ascending: the mesh is not in upper-triangular order");
+        for (int f = 0; f < m->nFaces; ++f)
+            CHECK(m->owner[f] >= 0 && m->owner[f] < m->nCells &&
+                      (f >= m->nInternalFaces || (m->neighbour[f] >= 0 && m->neighbour[f] < m->nCells)),
+                  SSAM_ERR_INVALID, "owner / neighbour label out of range");
+        if (computeCompactOrder(ctx, m, pm.perm)) {
+            permuteMesh(m, pm);
+            mm = *m;
+            mm.owner = pm.owner.data();
+            mm.neighbour = pm.neighbour.data();
+            mm.Sf = pm.Sf.data();
+            mm.weights = pm.w.data();
+            mm.V = pm.V.data();
+            mm.C = pm.C.data();
+            m = &mm;
+            permuted = true;
+        }
+    }
     ctx->nCells = m->nCells;
     ctx->nIF = m->nInternalFaces;
     ctx->nFaces = m->nFaces;
@@ -856,7 +1045,7 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     TRY(devAlloc(ctx, &ctx->V, nC + 4));
     CU(cudaMemcpyAsync(ctx->V, m->V, nC * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->sumV = 0.0;
-    for (size_t i = 0; i < nC; ++i) ctx->sumV += m->V[i];  // Foam::sum order; used by ssam_interface_delta_n
+    for (size_t i = 0; i < nC; ++i) ctx->sumV += callerMesh->V[i];  // Foam::sum order (the caller's cell order)
     TRY(devAlloc(ctx, &ctx->magSf_b, nB));
     TRY(devAlloc(ctx, &ctx->deltaCoeffs_b, nB));
     if (nB) {
@@ -891,8 +1080,24 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
         CU(cudaMemcpyAsync(ctx->haloSendCells + ctx->haloOffsets[p], ctx->owner + ctx->patchStart[patch],
                            size_t(ctx->patchSize[patch]) * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    if (permuted) {
+        TRY(devAlloc(ctx, &ctx->faceKey, size_t(ctx->nIF)));
+        CU(cudaMemcpyAsync(ctx->faceKey, pm.faceKey.data(), size_t(ctx->nIF) * sizeof(int), cudaMemcpyHostToDevice,
+                           ctx->stream));
+        TRY(devAlloc(ctx, &ctx->origOwner, nF));
+        TRY(devAlloc(ctx, &ctx->origNeighbour, size_t(ctx->nIF) + 8));
+        CU(cudaMemcpyAsync(ctx->origOwner, callerMesh->owner, nF * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->origNeighbour, callerMesh->neighbour, size_t(ctx->nIF) * sizeof(int),
+                           cudaMemcpyHostToDevice, ctx->stream));
+    }
     TRY(buildAddressing(ctx));
     if (ctx->nProcPatches == 0) TRY(buildTileOrder(ctx, m));
+    if (permuted) {
+        // from here on uploads / downloads of cell values go through the permutation
+        TRY(devAlloc(ctx, &ctx->perm, nC));
+        CU(cudaMemcpyAsync(ctx->perm, pm.perm.data(), nC * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->permHost.swap(pm.perm);
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
@@ -940,8 +1145,68 @@ static ssam_status ensureColouring(ssam_ctx* ctx) {
     return SSAM_OK;
 }
 
+// Tile-compact layout: the tables the getters expose are defined on the caller's numbering, so they are built
+// (on demand, by the same kernels) from the caller's owner/neighbour kept on the device, in a private context.
+static ssam_status ensureRefAddr(ssam_ctx* ctx) {
+    if (ctx->refAddr) return SSAM_OK;
+    ssam_ctx* r = new ssam_ctx;
+    r->device = ctx->device;
+    r->stream = ctx->stream;
+    r->blocking = true;
+    r->layoutMode = SSAM_LAYOUT_CALLER;
+    r->nCells = ctx->nCells;
+    r->nIF = ctx->nIF;
+    r->nFaces = ctx->nFaces;
+    r->nBnd = ctx->nBnd;
+    r->nTot = ctx->nTot;
+    r->nPatches = ctx->nPatches;
+    r->patchStart = ctx->patchStart;
+    r->patchSize = ctx->patchSize;
+    r->patchKind = ctx->patchKind;
+    r->patchNbrRank = ctx->patchNbrRank;
+    r->patchUbc = ctx->patchUbc;
+    r->haloPatch = ctx->haloPatch;
+    r->haloOffsets = ctx->haloOffsets;
+    r->nProcPatches = ctx->nProcPatches;
+    r->nProcFaces = ctx->nProcFaces;
+    r->haveMesh = true;
+    ctx->refAddr = r;
+    auto bail = [&](ssam_status st) {
+        ctx->err = r->err;
+        freeMesh(r);
+        delete r;
+        ctx->refAddr = nullptr;
+        return st;
+    };
+#define REF_TRY(x)                                  \
+    do {                                            \
+        ssam_status st_ = (x);                      \
+        if (st_ != SSAM_OK) return bail(st_);       \
+    } while (0)
+    REF_TRY(devAlloc(r, &r->owner, size_t(r->nFaces)));
+    REF_TRY(devAlloc(r, &r->neighbour, size_t(r->nIF) + 8));
+    REF_TRY(devAlloc(r, &r->bndFlags, size_t(r->nBnd)));
+    REF_TRY(devAlloc(r, &r->haloSendCells, size_t(r->nProcFaces)));
+    cudaMemcpyAsync(r->owner, ctx->origOwner, size_t(r->nFaces) * sizeof(int), cudaMemcpyDeviceToDevice, r->stream);
+    cudaMemcpyAsync(r->neighbour, ctx->origNeighbour, size_t(r->nIF) * sizeof(int), cudaMemcpyDeviceToDevice, r->stream);
+    if (r->nBnd)
+        cudaMemcpyAsync(r->bndFlags, ctx->bndFlags, size_t(r->nBnd), cudaMemcpyDeviceToDevice, r->stream);
+    for (int p = 0; p < r->nProcPatches; ++p) {
+        const int patch = r->haloPatch[size_t(p)];
+        cudaMemcpyAsync(r->haloSendCells + r->haloOffsets[size_t(p)], r->owner + r->patchStart[size_t(patch)],
+                        size_t(r->patchSize[size_t(patch)]) * sizeof(int), cudaMemcpyDeviceToDevice, r->stream);
+    }
+    REF_TRY(buildAddressing(r));
+#undef REF_TRY
+    return SSAM_OK;
+}
+
 ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n) {
     CHECK(ctx && ctx->haveMesh && n, SSAM_ERR_INVALID, "mesh not set");
+    if (which == SSAM_ADDR_CELL_ORDER) {
+        *n = ctx->nCells;
+        return SSAM_OK;
+    }
     switch (which) {
         case SSAM_ADDR_OWNER_START:
         case SSAM_ADDR_EXTRA_START:
@@ -963,6 +1228,17 @@ ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t 
     TRY(ssam_addressing_size(ctx, which, &have));
     CHECK(out && n == have, SSAM_ERR_INVALID, "size mismatch");
     if (n == 0) return SSAM_OK;
+    if (which == SSAM_ADDR_CELL_ORDER) {
+        for (int64_t i = 0; i < n; ++i) out[i] = ctx->permHost.empty() ? int32_t(i) : ctx->permHost[size_t(i)];
+        return SSAM_OK;
+    }
+    if (ctx->perm) {  // tables in the caller's numbering
+        TRY(ensureRefAddr(ctx));
+        ctx->refAddr->fricPatchCached = ctx->fricPatchCached;
+        const ssam_status st = ssam_addressing_get(ctx->refAddr, which, out, n);
+        if (st != SSAM_OK) ctx->err = ctx->refAddr->err;
+        return st;
+    }
     const int* src = nullptr;
     int* tmp = nullptr;
     switch (which) {
@@ -1224,8 +1500,15 @@ ssam_status ssam_face_field_download(ssam_ctx* ctx, int ff, double* internal_fac
     CHECK(ctx->faceField[ff] && ctx->faceFieldSet[ff], SSAM_ERR_MISSING_FIELD,
           "face field not available (nHatf: ssam_interface_correct, muf/nuf: ssam_mixture_muf/nuf)");
     const double* src = ctx->faceField[ff];
-    if (internal_faces && ctx->nIF)
-        CU(cudaMemcpyAsync(internal_faces, src, size_t(ctx->nIF) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (internal_faces && ctx->nIF) {
+        const double* from = src;
+        if (ctx->faceKey) {  // tile-compact layout: the device holds the internal faces in its own order
+            TRY(ensureStage(ctx, size_t(ctx->nIF)));
+            LAUNCH(k_scatter_by_key, gridFor(ctx->nIF, 256), 256, src, ctx->faceKey, ctx->nIF, ctx->stage);
+            from = ctx->stage;
+        }
+        CU(cudaMemcpyAsync(internal_faces, from, size_t(ctx->nIF) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (boundary_faces && ctx->nBnd)
         CU(cudaMemcpyAsync(boundary_faces, src + ctx->nIF, size_t(ctx->nBnd) * sizeof(double), cudaMemcpyDeviceToHost,
                            ctx->stream));
@@ -1491,33 +1774,15 @@ static ssam_status updateFusedHostSimple(ssam_ctx* ctx, const ssam_update_params
         if (!in.i) continue;
         TRY(ensureField(ctx, in.f));
         const int nc = ncompOf(in.f);
-        if (nc == 1) {
-            TRY(uploadAoS(ctx, in.i, ctx->nCells, 1, ctx->plane[in.f], 0));
-            if (in.b) TRY(uploadAoS(ctx, in.b, ctx->nBnd, 1, ctx->plane[in.f], ctx->nCells));
-        } else {
-            // one staging buffer holds internal + boundary AoS, two transposes, no intermediate sync
-            CU(cudaMemcpyAsync(ctx->stage, in.i, size_t(ctx->nCells) * nc * sizeof(double), cudaMemcpyHostToDevice,
-                               ctx->stream));
-            PlanePtrs pl;
-            for (int k = 0; k < 16; ++k) pl.p[k] = k < nc ? ctx->plane[in.f][k] : nullptr;
-            LAUNCH(k_aos_to_soa_n, gridFor((long long)ctx->nCells * nc, 256), 256, ctx->stage, ctx->nCells, nc, pl, 0);
-            if (in.b && ctx->nBnd) {
-                double* st2 = ctx->stage + size_t(ctx->nCells) * nc;
-                CU(cudaMemcpyAsync(st2, in.b, size_t(ctx->nBnd) * nc * sizeof(double), cudaMemcpyHostToDevice,
-                                   ctx->stream));
-                LAUNCH(k_aos_to_soa_n, gridFor((long long)ctx->nBnd * nc, 256), 256, st2, ctx->nBnd, nc, pl,
-                       ctx->nCells);
-            }
-        }
+        TRY(uploadAoS(ctx, in.i, ctx->nCells, nc, ctx->plane[in.f], 0));
+        if (in.b) TRY(uploadAoS(ctx, in.b, ctx->nBnd, nc, ctx->plane[in.f], ctx->nCells));
         ctx->isSet[in.f] = true;
     }
     TRY(updateFusedAsync(ctx, p, ctx->nProcPatches ? 2 : 0));
     for (int o = 0; o < io->nOut; ++o) {
         const int f = io->outFields[o];
         TRY(need(ctx, f, "requested output was not produced by this update"));
-        if (io->out_i && io->out_i[o])
-            CU(cudaMemcpyAsync(io->out_i[o], ctx->plane[f][0], size_t(ctx->nCells) * sizeof(double),
-                               cudaMemcpyDeviceToHost, ctx->stream));
+        if (io->out_i && io->out_i[o]) TRY(downloadAoS(ctx, io->out_i[o], ctx->nCells, 1, ctx->plane[f], 0));
         if (io->out_b && io->out_b[o] && ctx->nBnd)
             CU(cudaMemcpyAsync(io->out_b[o], ctx->plane[f][0] + ctx->nCells, size_t(ctx->nBnd) * sizeof(double),
                                cudaMemcpyDeviceToHost, ctx->stream));
@@ -1575,7 +1840,7 @@ static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_par
             double* stg = ctx->stage + size_t(k & 1) * chunkCells * 3;
             cudaMemcpyAsync(stg, io->U_i + size_t(c0) * 3, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice,
                             ctx->h2dStream);
-            k_aos_to_soa_n<<<gridFor((long long)n * 3, 256), 256, 0, ctx->h2dStream>>>(stg, n, 3, plU, c0);
+            k_aos_to_soa_n<<<gridFor((long long)n * 3, 256), 256, 0, ctx->h2dStream>>>(stg, n, 3, plU, c0, nullptr);
             ctx->launches++;
             for (int i = 1; i < 4; ++i)
                 if (hi[i])
@@ -1641,7 +1906,8 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
     // itself and its two neighbours)
     int nChunks = ctx->hostChunks >= 0 ? std::min(ctx->hostChunks, 64) : std::min(16, ctx->nTiles / 1024);
     while (nChunks > 1 && (ctx->nTiles + nChunks - 1) / nChunks < ctx->bandwidthTiles + 1) --nChunks;
-    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel == 1 && ctx->nTilesOversize == 0)
+    // (the pipeline moves contiguous cell ranges, which only exist in the caller's cell order)
+    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel == 1 && ctx->nTilesOversize == 0 && !ctx->perm)
         return updateFusedHostPipelined(ctx, p, io, nChunks);
     return updateFusedHostSimple(ctx, p, io);
 }

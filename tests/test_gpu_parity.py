@@ -402,3 +402,57 @@ def test_gpu_against_frozen_reference_source_outputs(ctx):
             check_field(f"{cname}/{key} vs reference sources", got, golden[cname + "/" + key], False)
             checked += 1
     assert checked >= 50
+
+
+@pytest.mark.parametrize("name", ["hex_natural", "hex_sheared", "poly", "nortonhoff"])
+def test_tile_compact_layout_is_bit_identical(name):
+    """The library's own cell order (SSAM_LAYOUT_COMPACT) is a pure data-layout change: every field, every face
+    field and every exposed integer table equals the caller-order layout bit for bit."""
+    mk = {"hex_natural": lambda: cases.cfg2(dims=(64, 32, 16)),
+          "hex_sheared": lambda: cases.cfg1(dims=(40, 24, 20), affine=SHEAR, grading=(2.0, 0.5, 3.0)),
+          "poly": lambda: cases.cfg3(base=(16, 16, 16)),
+          "nortonhoff": lambda: cases.cfg4(dims=(33, 21, 17))}[name]
+    case = mk()
+    m = case.mesh
+    res = {}
+    for mode in (P.LAYOUT_CALLER, P.LAYOUT_COMPACT):
+        with capi.Context(0) as c:
+            c.set_cell_layout(mode)
+            c.load_case(case)
+            assert c.layout_is_compact() == (mode == P.LAYOUT_COMPACT)
+            order = c.addressing(P.ADDR_CELL_ORDER)
+            assert np.array_equal(np.sort(order), np.arange(m.nCells))
+            if mode == P.LAYOUT_COMPACT:
+                assert not np.array_equal(order, np.arange(m.nCells))
+            out = {}
+            for variant in (0, 1):
+                c.set_cell_kernel(variant)
+                c.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+                for f in case.outputs + [P.F_GRADU, P.F_U]:
+                    gi, gb = c.download(f)
+                    out[(variant, f)] = np.concatenate([gi, gb])
+            c.set_cell_kernel(1)
+            c.interface_correct(c.interface_delta_n())
+            for f in (P.F_GRADALPHA, P.F_CURVATURE):
+                gi, gb = c.download(f)
+                out[("iface", f)] = np.concatenate([gi, gb])
+            out["nhatf"] = c.face_field(P.FF_NHATF, m.nInternalFaces, m.nBoundaryFaces)
+            for nuf, ff in ((False, P.FF_MUF), (True, P.FF_NUF)):
+                c.mixture_face_visc(case.params.mix, nuf)
+                out[("ff", ff)] = c.face_field(ff, m.nInternalFaces, m.nBoundaryFaces)
+            c.strain_rate(SR_FACTOR, P.F_STRAINRATE)
+            out["sr"] = np.concatenate(c.download(P.F_STRAINRATE))
+            out["minmax"] = np.array(c.field_min_max(P.F_T))
+            for which in range(P.ADDR_CELL_ORDER):
+                out[("addr", which)] = c.addressing(which)
+            # host-staged entry point (falls back to the unpipelined path under the compact layout)
+            _, ub = c.download(P.F_U)  # with the BC applied, as the device-resident update saw it
+            got = c.host_update(case, [P.F_NU, P.F_QVISC], U_b=ub)
+            out["host_nu"], out["host_qvisc"] = np.concatenate(got[P.F_NU]), np.concatenate(got[P.F_QVISC])
+            assert np.array_equal(out["host_nu"], out[(1, P.F_NU)])
+            res[mode] = out
+    a, b = res[P.LAYOUT_CALLER], res[P.LAYOUT_COMPACT]
+    assert a.keys() == b.keys()
+    for k in a:
+        same = (a[k] == b[k]) | ((a[k] != a[k]) & (b[k] != b[k]))
+        assert same.all(), f"{k}: {np.count_nonzero(~same)} values differ between the two layouts"
