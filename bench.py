@@ -19,6 +19,10 @@ Contract (one JSON line on stdout from rank 0):
 """
 from __future__ import annotations
 
+import os as _os
+
+# 5 MB halo messages: 4 NCCL channels are enough and leave more SMs to the interior tiles (profiles/r1_scaling.md)
+_os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
 import argparse
 import ctypes as C
 import json
@@ -360,7 +364,7 @@ def run_gpu(args):
                        "parallelism": f"slab{n_ranks}" if n_ranks > 1 else "single",
                        "l2": "inputs larger than L2 (%.2f GB touched per update vs 126 MB L2)" %
                              (case.bytes_per_update / 1e9),
-                       "cell_layout": layout_dev,
+                       "cell_layout": layout_dev, "halo_transport": ctx.halo_transport(),
                        "e2e_cell_layout": "caller order (host-staged mode)" if ctx_h is not ctx else layout_dev},
             "roofline": {"bound": "hbm", "kernel": "k_cells_tiled" if args.cell_kernel == 1 else "k_cells", "achieved": round(achieved, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,

@@ -363,6 +363,11 @@ SSAM_API ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int
 /* boundary values on processor patches <- neighbour rank's adjacent cell values, for every field
  * whose bit (1<<SSAM_F_*) is set in field_mask */
 SSAM_API ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t field_mask);
+/* Transport of the processor-patch exchanges: 1 = peer memory over NVLink (the pack kernel stores straight into the
+ * neighbour's IPC-mapped receive slot and publishes a flag; the receiver waits with a stream memory operation),
+ * 2 = grouped ncclSend/ncclRecv, 0 = not decided yet (before the first exchange) or no processor patches.
+ * Default is NCCL (measured faster on B200/NVSwitch); SSAM_HALO=p2p in the environment selects the peer-memory path. */
+SSAM_API int ssam_halo_transport(const ssam_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
     "ssam_face_field_device_ptr", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
-    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange",
+    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange", "ssam_halo_transport",
 ]
 
 
@@ -104,6 +104,7 @@ def load():
     L.ssam_comm_unique_id.argtypes = [vp]
     L.ssam_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ssam_halo_exchange.argtypes = [vp, C.c_uint32]
+    L.ssam_halo_transport.argtypes = [vp]
     _lib = L
     return L
 
@@ -170,6 +171,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.L.ssam_launch_count(self.h))
+
+    def halo_transport(self) -> str:
+        return {0: "none", 1: "peer-memory", 2: "nccl"}[self.L.ssam_halo_transport(self.h)]
 
     def set_cell_layout(self, mode: int):
         """0 = caller's cell order, 1 = tile-compact when it pays (default), 2 = always; before mesh_set"""

@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include <cuda.h>
+
 #include "nccl_dyn.h"
 #include "ssam_gpu.h"
 
@@ -37,6 +39,7 @@ struct ssam_ctx {
     int *tileListInterior = nullptr, *tileListCoupled = nullptr;
     int nTilesInterior = 0, nTilesCoupled = 0;
     int* tileOrder = nullptr;  // L2-friendly traversal order of the tiles (nullptr = natural order)
+    int4 *descInterior = nullptr, *descCoupled = nullptr, *descOrder = nullptr;  // tileDesc in list order
     int* tileIota = nullptr;  // identity tile list (chunked launches of the host-staged pipeline)
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaStream_t commStream = nullptr;
@@ -84,6 +87,18 @@ struct ssam_ctx {
     size_t sendCap = 0;
     ncclComm_t comm = nullptr;
     int rank = 0, nRanks = 1;
+    // halo exchange over peer memory (IPC-mapped receive slots); NCCL stays the fallback
+    struct P2P {
+        int state = 0;  // 0 = not tried, 1 = on, -1 = unavailable (NCCL path)
+        double* recvBuf = nullptr;  // [256 B of flag words][2 slots of slotDoubles]
+        size_t slotDoubles = 0;
+        unsigned* done = nullptr;
+        int* patchB0 = nullptr;
+        void* peerMap[32] = {nullptr};      // IPC mappings this context opened (one per neighbour rank)
+        double* peerBase[32] = {nullptr};   // per processor patch: the neighbour's receive buffer
+        int peerOff[32] = {0};
+        unsigned long long seq = 0;
+    } p2p;
 
     // optional per-kernel timing (ssam_profile_enable)
     bool profile = false;
@@ -186,6 +201,19 @@ ssam_status ensureFaceField(ssam_ctx* ctx, int ff) {
     return SSAM_OK;
 }
 
+void p2pFree(ssam_ctx* c) {
+    for (void*& b : c->p2p.peerMap) {
+        if (b) cudaIpcCloseMemHandle(b);
+        b = nullptr;
+    }
+    for (double*& b : c->p2p.peerBase) b = nullptr;
+    devFree(c->p2p.recvBuf);
+    devFree(c->p2p.done);
+    devFree(c->p2p.patchB0);
+    c->p2p.state = 0;
+    c->p2p.seq = 0;
+}
+
 void freeMesh(ssam_ctx* c) {
     if (c->refAddr) {
         freeMesh(c->refAddr);
@@ -201,6 +229,9 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->tileDesc);
     devFree(c->tileIota);
     devFree(c->tileOrder);
+    devFree(c->descInterior);
+    devFree(c->descCoupled);
+    devFree(c->descOrder);
     devFree(c->perm);
     devFree(c->faceKey);
     devFree(c->origOwner);
@@ -223,6 +254,7 @@ void freeMesh(ssam_ctx* c) {
         for (auto& p : c->plane[f]) devFree(p);
         c->isSet[f] = false;
     }
+    p2pFree(c);
     devFree(c->haloSendCells);
     devFree(c->sendBuf);
     c->sendCap = 0;
@@ -335,6 +367,14 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
         if (!lc.empty())
             CU(cudaMemcpyAsync(ctx->tileListCoupled, lc.data(), lc.size() * sizeof(int), cudaMemcpyHostToDevice,
                                ctx->stream));
+        TRY(devAlloc(ctx, &ctx->descInterior, li.size()));
+        TRY(devAlloc(ctx, &ctx->descCoupled, lc.size()));
+        if (!li.empty())
+            LAUNCH(k_tile_desc_list, gridFor((long long)li.size(), 256), 256, ctx->tileDesc, ctx->tileListInterior,
+                   int(li.size()), ctx->descInterior);
+        if (!lc.empty())
+            LAUNCH(k_tile_desc_list, gridFor((long long)lc.size(), 256), 256, ctx->tileDesc, ctx->tileListCoupled,
+                   int(lc.size()), ctx->descCoupled);
     }
     CU(cudaStreamSynchronize(ctx->stream));
     cudaFree(cursor);
@@ -448,9 +488,158 @@ void fillMeshArgs(ssam_ctx* c, UpdateArgs& a) {
 // processorFvPatchField::evaluate for several fields at once: ONE pack kernel gathers field[faceCells] of
 // every processor patch for all component planes, ONE NCCL group sends each (patch, plane) run and
 // receives straight into the boundary part of the planes.
+// stream memory operation: wait until *addr >= value without occupying an SM (driver entry point, no libcuda link)
+typedef CUresult (*StreamWaitValue64Fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+StreamWaitValue64Fn streamWaitValue64() {
+    static StreamWaitValue64Fn fn = []() -> StreamWaitValue64Fn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<StreamWaitValue64Fn>(p);
+    }();
+    return fn;
+}
+
+// One-time (per mesh) collective set-up of the peer-memory halo path: every rank allocates a receive buffer, the
+// neighbours swap IPC handles and slot offsets through NCCL, and all ranks agree (all-reduce) on whether it works.
+ssam_status p2pSetup(ssam_ctx* ctx) {
+    auto& P = ctx->p2p;
+    P.state = -1;
+    // measured on 2 B200s (profiles/r1_scaling.md): the NCCL exchange is 12 us per step faster than this path, so
+    // NCCL is the default and the peer-memory path is opt-in (SSAM_HALO=p2p)
+    const char* env = std::getenv("SSAM_HALO");
+    int ok = (env && std::string(env) == "p2p") ? 1 : 0;
+    if (!streamWaitValue64()) ok = 0;
+    NcclApi& N = nccl();
+    const int nP = ctx->nProcPatches;
+    struct Msg {
+        cudaIpcMemHandle_t handle;
+        int off, size, pad[14];
+    };
+    static_assert(sizeof(Msg) == 128, "handshake message size");
+    std::vector<Msg> mine(static_cast<size_t>(nP)), theirs(static_cast<size_t>(nP));
+    P.slotDoubles = size_t(ctx->nProcFaces) * 16;
+    const size_t total = 32 + 2 * P.slotDoubles;  // 32 doubles = 256 B of flag words
+    if (cudaMalloc(reinterpret_cast<void**>(&P.recvBuf), total * sizeof(double)) != cudaSuccess) ok = 0;
+    cudaIpcMemHandle_t h;
+    std::memset(&h, 0, sizeof(h));
+    if (ok && cudaIpcGetMemHandle(&h, P.recvBuf) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    if (P.recvBuf) CU(cudaMemsetAsync(P.recvBuf, 0, total * sizeof(double), ctx->stream));
+    TRY(devAlloc(ctx, &P.done, 1));
+    CU(cudaMemsetAsync(P.done, 0, sizeof(unsigned), ctx->stream));
+    std::vector<int> b0(static_cast<size_t>(nP) + 1, 0);
+    for (int p = 0; p < nP; ++p) {
+        const int patch = ctx->haloPatch[size_t(p)];
+        b0[size_t(p)] = ctx->patchStart[size_t(patch)] - ctx->nIF;
+        std::memset(&mine[size_t(p)], 0, sizeof(Msg));
+        mine[size_t(p)].handle = h;
+        mine[size_t(p)].off = ctx->haloOffsets[size_t(p)];
+        mine[size_t(p)].size = ctx->haloOffsets[size_t(p) + 1] - ctx->haloOffsets[size_t(p)];
+    }
+    TRY(devAlloc(ctx, &P.patchB0, size_t(nP) + 1));
+    CU(cudaMemcpyAsync(P.patchB0, b0.data(), (size_t(nP) + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    // handshake with every neighbour (device staging buffers, one grouped send/recv)
+    char* dmsg = nullptr;
+    TRY(devAlloc(ctx, &dmsg, size_t(2 * nP) * sizeof(Msg)));
+    CU(cudaMemcpyAsync(dmsg, mine.data(), size_t(nP) * sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream));
+    NC(N.GroupStart());
+    for (int p = 0; p < nP; ++p) {
+        const int peer = ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(p)])];
+        NC(N.Send(dmsg + size_t(p) * sizeof(Msg), sizeof(Msg), ncclChar, peer, ctx->comm, ctx->stream));
+        NC(N.Recv(dmsg + size_t(nP + p) * sizeof(Msg), sizeof(Msg), ncclChar, peer, ctx->comm, ctx->stream));
+    }
+    NC(N.GroupEnd());
+    CU(cudaMemcpyAsync(theirs.data(), dmsg + size_t(nP) * sizeof(Msg), size_t(nP) * sizeof(Msg), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < nP && ok; ++p) {
+        if (theirs[size_t(p)].size != mine[size_t(p)].size) {
+            ok = 0;
+            break;
+        }
+        // two patches towards the same neighbour share one mapping
+        void* base = nullptr;
+        for (int q = 0; q < p; ++q)
+            if (ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(q)])] == ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(p)])])
+                base = P.peerBase[q];
+        if (!base) {
+            if (cudaIpcOpenMemHandle(&base, theirs[size_t(p)].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            P.peerMap[p] = base;
+        }
+        P.peerBase[p] = static_cast<double*>(base);
+        P.peerOff[p] = theirs[size_t(p)].off;
+    }
+    if (ctx->nRanks > 32) ok = 0;  // one flag word per neighbour rank, 32 words
+    // every rank must take the same path
+    int* dflag = reinterpret_cast<int*>(dmsg);
+    CU(cudaMemcpyAsync(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    NC(N.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, ctx->comm, ctx->stream));
+    CU(cudaMemcpyAsync(&ok, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dmsg);
+    if (!ok) {
+        p2pFree(ctx);
+        P.state = -1;
+        return SSAM_OK;
+    }
+    P.state = 1;
+    P.seq = 0;
+    return SSAM_OK;
+}
+
+ssam_status haloExchangePeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStream_t stream) {
+    auto& P = ctx->p2p;
+    const unsigned long long seq = ++P.seq;
+    const size_t slot = size_t(seq & 1ull);
+    PeerLayout L;
+    L.nPatches = ctx->nProcPatches;
+    for (int p = 0; p <= ctx->nProcPatches; ++p) L.offsets[p] = ctx->haloOffsets[size_t(p)];
+    for (int p = 0; p < ctx->nProcPatches; ++p) {
+        double* base = P.peerBase[p];
+        L.dst[p] = base + 32 + slot * P.slotDoubles;
+        L.dstOff[p] = P.peerOff[p];
+        // the neighbour's flag word for this rank: indexed by this rank's number modulo 32
+        L.flag[p] = reinterpret_cast<unsigned long long*>(base) + (ctx->rank & 31);
+    }
+    const int grid = gridFor((long long)ctx->nProcFaces * nc, 256);
+    k_halo_pack_peer<<<grid, 256, 0, stream>>>(ctx->haloSendCells, L, nc, pl, P.done, seq);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    StreamWaitValue64Fn wait = streamWaitValue64();
+    for (int p = 0; p < ctx->nProcPatches; ++p) {
+        const int peer = ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(p)])];
+        bool seen = false;
+        for (int q = 0; q < p; ++q) seen |= ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(q)])] == peer;
+        if (seen) continue;
+        const CUdeviceptr addr = reinterpret_cast<CUdeviceptr>(reinterpret_cast<unsigned long long*>(P.recvBuf) + (peer & 31));
+        CHECK(wait(reinterpret_cast<CUstream>(stream), addr, seq, CU_STREAM_WAIT_VALUE_GEQ) == CUDA_SUCCESS, SSAM_ERR_CUDA,
+              "cuStreamWaitValue64 failed");
+    }
+    HaloLayout H;
+    H.nPatches = ctx->nProcPatches;
+    for (int p = 0; p <= ctx->nProcPatches; ++p) H.offsets[p] = ctx->haloOffsets[size_t(p)];
+    k_halo_unpack<<<grid, 256, 0, stream>>>(P.recvBuf + 32 + slot * P.slotDoubles, H, nc, pl, ctx->nCells, P.patchB0);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SSAM_OK;
+}
+
 ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cudaStream_t stream) {
     if (ctx->nProcPatches == 0 || nFields == 0) return SSAM_OK;
     CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
+    if (ctx->p2p.state == 0) {
+        // collective: every rank reaches its first exchange in the same call
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (ctx->commStream) CU(cudaStreamSynchronize(ctx->commStream));
+        TRY(p2pSetup(ctx));
+    }
     PlanePtrs pl;
     int nc = 0;
     for (int i = 0; i < nFields; ++i) {
@@ -461,6 +650,7 @@ ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cu
         }
     }
     for (int k = nc; k < 16; ++k) pl.p[k] = nullptr;
+    if (ctx->p2p.state == 1) return haloExchangePeer(ctx, pl, nc, stream);
     const size_t needBuf = size_t(ctx->nProcFaces) * 16;
     if (ctx->sendCap < needBuf) {
         CU(cudaStreamSynchronize(ctx->stream));
@@ -563,6 +753,17 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
     UpdateArgs a = a0;
     a.tileList = list;
     a.tileCount = count;
+    if (LIST) {
+        if (list == ctx->tileListInterior) {
+            a.tileDesc = ctx->descInterior;
+        } else if (list == ctx->tileListCoupled) {
+            a.tileDesc = ctx->descCoupled;
+        } else if (list == ctx->tileOrder) {
+            a.tileDesc = ctx->descOrder;
+        } else {
+            a.tileDesc = ctx->tileDesc + (list - ctx->tileIota);  // a range of the identity list
+        }
+    }
     static bool configured[64] = {false};  // per device: the attribute belongs to the device's context
     const int smem = int(sizeof(TileSmem));
     if (!configured[ctx->device & 63]) {
@@ -699,6 +900,8 @@ ssam_status buildTileOrder(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     }
     TRY(devAlloc(ctx, &ctx->tileOrder, size_t(nT)));
     CU(cudaMemcpyAsync(ctx->tileOrder, order.data(), size_t(nT) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(devAlloc(ctx, &ctx->descOrder, size_t(nT)));
+    LAUNCH(k_tile_desc_list, gridFor(nT, 256), 256, ctx->tileDesc, ctx->tileOrder, nT, ctx->descOrder);
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
@@ -1723,6 +1926,12 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         CU(cudaStreamWaitEvent(ctx->commStream, ctx->evMainToComm, 0));
         if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->commStream));
         TRY(launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream));
+        static const bool profInterior = std::getenv("SSAM_PROFILE_INTERIOR") != nullptr;  // experiments only
+        if (ctx->profile && profInterior && ev1) {
+            CU(cudaEventRecord(ev1, ctx->stream));
+            ctx->profEvents.emplace_back(ev0, ev1);
+            ev0 = ev1 = nullptr;
+        }
         TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->commStream));
         TRY(haloExchangeFields(ctx, outs2, n2, ctx->commStream));
         CU(cudaEventRecord(ctx->evCommToMain, ctx->commStream));
@@ -1743,7 +1952,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         }
         if (ctx->nProcPatches) TRY(haloExchangeFields(ctx, outs2, n2, ctx->stream));
     }
-    if (ctx->profile) {
+    if (ctx->profile && ev1) {
         CU(cudaEventRecord(ev1, ctx->stream));
         ctx->profEvents.emplace_back(ev0, ev1);
     }
@@ -1958,6 +2167,11 @@ ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int nRanks) 
     ctx->nRanks = nRanks;
     ctx->fricPatchCached = -1;
     return SSAM_OK;
+}
+
+int ssam_halo_transport(const ssam_ctx* ctx) {
+    if (!ctx || ctx->nProcPatches == 0 || ctx->p2p.state == 0) return 0;
+    return ctx->p2p.state == 1 ? 1 : 2;
 }
 
 ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t mask) {

@@ -130,7 +130,7 @@ def main():
     n_proc = int(sum(case.mesh.patchSize[p] for p in range(case.mesh.nPatches) if case.mesh.patchKind[p] == 1))
     dist.barrier()
     print(f"[rank {rank}/{world}] {args.decomp}: {case.mesh.nCells} cells, {n_proc} processor faces, "
-          f"worst rel err {worst:.2e} -- OK", flush=True)
+          f"halo transport {ctx.halo_transport()}, worst rel err {worst:.2e} -- OK", flush=True)
     ctx.close()
     dist.destroy_process_group()
 
