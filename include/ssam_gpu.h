@@ -209,6 +209,11 @@ SSAM_API ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant);
  * The chunk-pipelined ssam_update_fused_host needs SSAM_LAYOUT_CALLER (it falls back to unpipelined otherwise). */
 enum { SSAM_LAYOUT_CALLER = 0, SSAM_LAYOUT_AUTO = 1, SSAM_LAYOUT_COMPACT = 2 };
 SSAM_API ssam_status ssam_set_cell_layout(ssam_ctx* ctx, int mode);
+/* Host-only helper (no context, no GPU): the tile-compact order ssam_mesh_set would compute for this mesh
+ * (order[i] = caller cell held at device position i), the out-of-tile neighbours per cell before and after, and
+ * whether SSAM_LAYOUT_AUTO would adopt it. */
+SSAM_API ssam_status ssam_compact_cell_order(const ssam_mesh_desc* mesh, int32_t* order, double* remote_caller,
+                                             double* remote_compact, int* would_use);
 /* 1 when the current mesh is held in tile-compact order */
 SSAM_API int ssam_cell_layout_is_compact(const ssam_ctx* ctx);
 /* Per-kernel timing for the roofline figure: when enabled, every fused update brackets its cell

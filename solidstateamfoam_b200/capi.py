@@ -18,7 +18,7 @@ _lib = None
 # every exported symbol of include/ssam_gpu.h (checked by tests/test_abi_symbols.py)
 SYMBOLS = [
     "ssam_create", "ssam_destroy", "ssam_last_error", "ssam_sync", "ssam_set_stream", "ssam_set_blocking",
-    "ssam_abi_version", "ssam_launch_count", "ssam_set_cell_kernel", "ssam_set_cell_layout", "ssam_cell_layout_is_compact", "ssam_profile_enable", "ssam_profile_get", "ssam_mesh_set", "ssam_patch_u_bc_set", "ssam_addressing_size",
+    "ssam_abi_version", "ssam_launch_count", "ssam_set_cell_kernel", "ssam_set_cell_layout", "ssam_cell_layout_is_compact", "ssam_compact_cell_order", "ssam_profile_enable", "ssam_profile_get", "ssam_mesh_set", "ssam_patch_u_bc_set", "ssam_addressing_size",
     "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
@@ -64,6 +64,7 @@ def load():
     L.ssam_set_cell_kernel.argtypes = [vp, C.c_int]
     L.ssam_set_cell_layout.argtypes = [vp, C.c_int]
     L.ssam_cell_layout_is_compact.argtypes = [vp]
+    L.ssam_compact_cell_order.argtypes = [C.POINTER(P.MeshDesc), ip, dp, dp, C.POINTER(C.c_int)]
     L.ssam_profile_enable.argtypes = [vp, C.c_int]
     L.ssam_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.ssam_mesh_set.argtypes = [vp, C.POINTER(P.MeshDesc)]
@@ -122,6 +123,19 @@ def _f64(a, shape=None):
 
 FUSED_WRITE_GRAD = 1
 FUSED_HALO_INPUTS = 2
+
+
+def compact_cell_order(mesh):
+    """host-only: (order, remote neighbours per cell before, after, would SSAM_LAYOUT_AUTO use it)"""
+    L = load()
+    desc, keep = P.mesh_desc(mesh)
+    order = np.zeros(mesh.nCells, dtype=np.int32)
+    a, b, use = C.c_double(), C.c_double(), C.c_int()
+    st = L.ssam_compact_cell_order(C.byref(desc), order.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(a), C.byref(b),
+                                   C.byref(use))
+    if st != 0:
+        raise SsamError(st, L.ssam_last_error(None).decode())
+    return order, a.value, b.value, bool(use.value)
 
 
 class Context:

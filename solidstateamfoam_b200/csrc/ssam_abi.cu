@@ -923,7 +923,8 @@ struct PermutedMesh {
 };
 
 // -> perm (library position -> caller cell); returns false when clustering does not pay
-bool computeCompactOrder(ssam_ctx* ctx, const ssam_mesh_desc* m, std::vector<int>& perm) {
+bool computeCompactOrder(int layoutMode, const ssam_mesh_desc* m, std::vector<int>& perm, double& remotePerCellCaller,
+                         double& remotePerCellCompact) {
     const int nC = m->nCells, nIF = m->nInternalFaces;
     const int nB = (nC + RUN - 1) / RUN;
     std::vector<std::vector<int>> nb(nB);
@@ -1004,10 +1005,10 @@ bool computeCompactOrder(ssam_ctx* ctx, const ssam_mesh_desc* m, std::vector<int
     long long remoteCompact = 0;
     for (int f = 0; f < nIF; ++f)
         if (inv[size_t(m->owner[f])] / TILE != inv[size_t(m->neighbour[f])] / TILE) remoteCompact += 2;
-    ctx->remotePerCellCaller = double(remoteCaller) / nC;
-    ctx->remotePerCellCompact = double(remoteCompact) / nC;
+    remotePerCellCaller = double(remoteCaller) / nC;
+    remotePerCellCompact = double(remoteCompact) / nC;
     // pays when at least one gather per cell moves from global memory into the tile
-    return ctx->layoutMode == 2 || ctx->remotePerCellCaller - ctx->remotePerCellCompact >= 1.0;
+    return layoutMode == 2 || remotePerCellCaller - remotePerCellCompact >= 1.0;
 }
 
 void permuteMesh(const ssam_mesh_desc* m, PermutedMesh& pm) {
@@ -1144,6 +1145,24 @@ ssam_status ssam_set_cell_layout(ssam_ctx* ctx, int mode) {
 }
 int ssam_cell_layout_is_compact(const ssam_ctx* ctx) { return (ctx && ctx->perm) ? 1 : 0; }
 
+// host-only: the order ssam_mesh_set would use (no context, no GPU)
+ssam_status ssam_compact_cell_order(const ssam_mesh_desc* m, int32_t* order, double* remote_caller,
+                                    double* remote_compact, int* would_use) {
+    if (!m || !order || m->nCells <= 0 || !m->owner || (m->nInternalFaces > 0 && !m->neighbour))
+        return fail(nullptr, SSAM_ERR_INVALID, "null / empty mesh");
+    for (int f = 0; f < m->nInternalFaces; ++f)
+        if (m->owner[f] < 0 || m->owner[f] >= m->nCells || m->neighbour[f] < 0 || m->neighbour[f] >= m->nCells)
+            return fail(nullptr, SSAM_ERR_INVALID, "owner / neighbour label out of range");
+    std::vector<int> perm;
+    double a = 0, b = 0;
+    const bool use = computeCompactOrder(SSAM_LAYOUT_AUTO, m, perm, a, b);
+    for (int i = 0; i < m->nCells; ++i) order[i] = perm[size_t(i)];
+    if (remote_caller) *remote_caller = a;
+    if (remote_compact) *remote_compact = b;
+    if (would_use) *would_use = (use && m->nCells >= 2 * TILE) ? 1 : 0;
+    return SSAM_OK;
+}
+
 ssam_status ssam_profile_enable(ssam_ctx* ctx, int enable) {
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     ctx->profile = enable != 0;
@@ -1191,7 +1210,7 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
             CHECK(m->owner[f] >= 0 && m->owner[f] < m->nCells &&
                       (f >= m->nInternalFaces || (m->neighbour[f] >= 0 && m->neighbour[f] < m->nCells)),
                   SSAM_ERR_INVALID, "owner / neighbour label out of range");
-        if (computeCompactOrder(ctx, m, pm.perm)) {
+        if (computeCompactOrder(ctx->layoutMode, m, pm.perm, ctx->remotePerCellCaller, ctx->remotePerCellCompact)) {
             permuteMesh(m, pm);
             mm = *m;
             mm.owner = pm.owner.data();
