@@ -356,6 +356,12 @@ def run_gpu(args):
         bytes_cells = case.bytes_per_update - 40 * n_fric
         cells_avg_ms = cells_ms / max(cells_n, 1)
         achieved = bytes_cells / (cells_avg_ms * 1e-3) / 1e9
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this workload and layout, if any
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = tr.get(args.workload, {}).get(layout_dev, {}).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": n_ranks, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True,
@@ -367,7 +373,7 @@ def run_gpu(args):
                        "cell_layout": layout_dev, "halo_transport": ctx.halo_transport(),
                        "e2e_cell_layout": "caller order (host-staged mode)" if ctx_h is not ctx else layout_dev},
             "roofline": {"bound": "hbm", "kernel": "k_cells_tiled" if args.cell_kernel == 1 else "k_cells", "achieved": round(achieved, 1), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic if n_ranks == 1 else None,
                          "algorithmic_bytes_per_launch": bytes_cells, "kernel_ms": round(cells_avg_ms, 4),
                          "kernel_share_of_step": round(cells_avg_ms / (ms_total / args.steps), 4),
                          "peak_source": peak_src},

@@ -1705,11 +1705,35 @@ ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags)
     a.deltaN = deltaN;
     const int gc = gridFor(ctx->nCells, 256), gb = gridFor(ctx->nBnd, 128), gf = gridFor(ctx->nFaces, 256);
     if (ctx->nProcPatches && (flags & 2)) TRY(haloExchangeField(ctx, SSAM_F_ALPHA1));
-    LAUNCH(k_iface_grad_cells, gc, 256, a);
+    const bool tiled = ctx->cellKernel >= 1 && ctx->nTilesOversize == 0;
+    a.tileDesc = ctx->tileDesc;
+    a.tileCount = ctx->nTiles;
+    a.pfDist = ctx->pfDist;
+    a.pfDistU = a.pfDist + ctx->bandwidthTiles;
+    const int smem = int(sizeof(TileSmem));
+    if (tiled) {
+        static bool configured[64] = {false};
+        if (!configured[ctx->device & 63]) {
+            CU(cudaFuncSetAttribute(k_iface_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(k_iface_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured[ctx->device & 63] = true;
+        }
+        k_iface_tiled<0><<<ctx->nTiles, TILE, smem, ctx->stream>>>(a);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    } else {
+        LAUNCH(k_iface_grad_cells, gc, 256, a);
+    }
     if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_GRADALPHA));
     if (ctx->nBnd) LAUNCH(k_iface_grad_bnd, gb, 128, a);
-    LAUNCH(k_iface_nhatf, gf, 256, a);
-    LAUNCH(k_iface_div_cells, gc, 256, a);
+    if (tiled) {
+        k_iface_tiled<1><<<ctx->nTiles, TILE, smem, ctx->stream>>>(a);
+        ctx->launches++;
+        CU(cudaGetLastError());
+    } else {
+        LAUNCH(k_iface_nhatf, gf, 256, a);
+        LAUNCH(k_iface_div_cells, gc, 256, a);
+    }
     if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_CURVATURE));
     ctx->isSet[SSAM_F_GRADALPHA] = ctx->isSet[SSAM_F_CURVATURE] = true;
     ctx->faceFieldSet[SSAM_FF_NHATF] = true;

@@ -281,8 +281,9 @@ def test_stress_strain_post_processing(ctx, name):
     assert np.array_equal(np.concatenate([gi, gb]), oc.field(P.F_SIGMAVM))  # pure IEEE arithmetic
 
 
+@pytest.mark.parametrize("variant", [0, 1], ids=["direct", "tiled"])
 @pytest.mark.parametrize("name", ["cfg1_hex", "cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly"])
-def test_interface_correct_matches_oracle(ctx, name):
+def test_interface_correct_matches_oracle(ctx, name, variant):
     """interfaceProperties::correct() (SURVEY 8f-2): gradAlpha, nHatf, K -- pure IEEE arithmetic in the
     reference's summation order, so every value is bit-exact."""
     case = small_cases()[name]()
@@ -291,7 +292,11 @@ def test_interface_correct_matches_oracle(ctx, name):
     oc = oracle_case(case, apply_bc=False)
     dn = ctx.interface_delta_n()
     assert dn == O.interface_delta_n([oc])
-    ctx.interface_correct(dn)
+    ctx.set_cell_kernel(variant)
+    try:
+        ctx.interface_correct(dn)
+    finally:
+        ctx.set_cell_kernel(1)
     oc.interface_correct(dn)
     for f in (P.F_GRADALPHA, P.F_CURVATURE):
         gi, gb = ctx.download(f)
