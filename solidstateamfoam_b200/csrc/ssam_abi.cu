@@ -40,6 +40,7 @@ struct ssam_ctx {
     int nTilesInterior = 0, nTilesCoupled = 0;
     int* tileOrder = nullptr;  // L2-friendly traversal order of the tiles (nullptr = natural order)
     int4 *descInterior = nullptr, *descCoupled = nullptr, *descOrder = nullptr;  // tileDesc in list order
+    int interiorRange0 = -1;  // >= 0: the interior tiles are the contiguous range [interiorRange0, +nTilesInterior)
     int* tileIota = nullptr;  // identity tile list (chunked launches of the host-staged pipeline)
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaStream_t commStream = nullptr;
@@ -359,6 +360,9 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
         for (int t = 0; t < ctx->nTiles; ++t) (h[t] ? lc : li).push_back(t);
         ctx->nTilesInterior = int(li.size());
         ctx->nTilesCoupled = int(lc.size());
+        // a contiguous interior range (slab partitions in the tile-compact order) needs no list indirection, which
+        // costs the cell kernel 4-5 % (profiles/r1_scaling.md)
+        ctx->interiorRange0 = (!li.empty() && li.back() - li.front() + 1 == int(li.size())) ? li.front() : -1;
         TRY(devAlloc(ctx, &ctx->tileListInterior, li.size()));
         TRY(devAlloc(ctx, &ctx->tileListCoupled, lc.size()));
         if (!li.empty())
@@ -1968,7 +1972,13 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->commStream, ctx->evMainToComm, 0));
         if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->commStream));
-        TRY(launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream));
+        if (ctx->interiorRange0 >= 0) {
+            UpdateArgs ar = a;
+            ar.tileOffset = ctx->interiorRange0;
+            TRY(launchCellsTiled(ctx, ar, model1, nullptr, ctx->nTilesInterior, ctx->stream));
+        } else {
+            TRY(launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream));
+        }
         static const bool profInterior = std::getenv("SSAM_PROFILE_INTERIOR") != nullptr;  // experiments only
         if (ctx->profile && profInterior && ev1) {
             CU(cudaEventRecord(ev1, ctx->stream));
