@@ -312,7 +312,8 @@ enum {
     SSAM_FF_NHATF = 0, /* interfaceProperties::nHatf_                                                   */
     SSAM_FF_MUF = 1,   /* incompressibleTwoPhaseThermalMixture::muf()  (…Mixture.C:163-180)              */
     SSAM_FF_NUF = 2,   /* incompressibleTwoPhaseThermalMixture::nuf()  (…Mixture.C:183-202)              */
-    SSAM_FF_COUNT = 3
+    SSAM_FF_KF = 3,    /* fvc::interpolate(kf): the face conductivity fvm::laplacian(kf, temp) uses (fluid/TEqn.H:22)  */
+    SSAM_FF_COUNT = 4
 };
 SSAM_API ssam_status ssam_face_field_download(ssam_ctx* ctx, int face_field, double* internal_faces,
                                               double* boundary_faces);
@@ -320,6 +321,9 @@ SSAM_API double* ssam_face_field_device_ptr(ssam_ctx* ctx, int face_field);
 /* muf()/nuf(): alpha1f = min(max(fvc::interpolate(alpha1),0),1);
  *   muf = alpha1f*rho1*interpolate(nu1) + (1-alpha1f)*rho2*interpolate(nu2);  nuf = muf/(alpha1f*rho1+(1-alpha1f)*rho2)
  * linear interpolation; reads ALPHA1, NU1, NU2 (processor-patch boundary values as left by the last update). */
+/* fvc::interpolate(vf) with the linear scheme for any scalar field (internal faces w*(P-N)+N, processor faces
+ * w*P+(1-w)*N_b, other boundary faces the boundary value) -> face field slot `face_field`. */
+SSAM_API ssam_status ssam_face_interpolate(ssam_ctx* ctx, int field, int face_field);
 SSAM_API ssam_status ssam_mixture_muf(ssam_ctx* ctx, const ssam_mixture_params* p);
 SSAM_API ssam_status ssam_mixture_nuf(ssam_ctx* ctx, const ssam_mixture_params* p);
 /* min(vf).value(), max(vf).value() over internal and boundary values and over all ranks, as printed by

@@ -1182,6 +1182,17 @@ void orc_friction_patch_centre(orc_case* h, double* centre3, double* area) {
     std::memcpy(centre3, CASE(h).fricCentre, 3 * sizeof(double));
     *area = CASE(h).fricArea;
 }
+// fvc::interpolate(field) (linear) into out[nFaces]
+int orc_face_interpolate(orc_case* h, int field, double* out) {
+    Case& c = CASE(h);
+    if (field < 0 || field >= SSAM_F_COUNT || ncompOf(field) != 1 || !c.set[field]) {
+        c.err = "scalar field not set";
+        return SSAM_ERR_MISSING_FIELD;
+    }
+    const Fld sf = interpolateLinear(c, c.f[field]);
+    std::memcpy(out, sf.data(), sf.size() * sizeof(double));
+    return 0;
+}
 int orc_mixture_face_visc(orc_case* h, const ssam_mixture_params* p, int nuf) { return mixtureFaceVisc(CASE(h), *p, nuf != 0); }
 double* orc_face_field(orc_case* h, int which) {
     Case& c = CASE(h);

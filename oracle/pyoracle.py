@@ -46,6 +46,7 @@ def lib():
             getattr(L, "orc_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams), C.c_int]
+        L.orc_face_interpolate.argtypes = [vp, C.c_int, dp]
         L.orc_mixture_face_visc.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
         L.orc_face_field.restype = dp
         L.orc_face_field.argtypes = [vp, C.c_int]
@@ -153,6 +154,12 @@ class OracleCase:
 
     def nhatf(self):
         return np.ctypeslib.as_array(lib().orc_interface_nhatf(self.h), shape=(self.mesh.nFaces,)).copy()
+
+    def face_interpolate(self, field):
+        """fvc::interpolate(field), linear scheme -> [nFaces]"""
+        out = np.zeros(self.mesh.nFaces)
+        self._chk(lib().orc_face_interpolate(self.h, field, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def mixture_face_visc(self, p, nuf=False):
         """muf() / nuf(): returns the surfaceScalarField (internal faces then boundary faces)."""

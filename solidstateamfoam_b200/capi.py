@@ -24,7 +24,7 @@ SYMBOLS = [
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
-    "ssam_face_field_device_ptr", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
+    "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange", "ssam_halo_transport",
 ]
 
@@ -93,6 +93,7 @@ def load():
     L.ssam_face_field_download.argtypes = [vp, C.c_int, dp, dp]
     L.ssam_face_field_device_ptr.restype = C.c_void_p
     L.ssam_face_field_device_ptr.argtypes = [vp, C.c_int]
+    L.ssam_face_interpolate.argtypes = [vp, C.c_int, C.c_int]
     L.ssam_mixture_muf.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_mixture_nuf.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_field_min_max.argtypes = [vp, C.c_int, dp, dp]
@@ -294,6 +295,10 @@ class Context:
         bi = out[n_internal_faces:]
         self._chk(self.L.ssam_face_field_download(self.h, which, _dptr(out), _dptr(bi) if n_boundary_faces else None))
         return out
+
+    def face_interpolate(self, field: int, face_field: int):
+        """fvc::interpolate(field) (linear) -> face field slot"""
+        self._chk(self.L.ssam_face_interpolate(self.h, field, face_field))
 
     def mixture_face_visc(self, p: P.MixtureParams, nuf: bool = False):
         """muf() / nuf() -> FF_MUF / FF_NUF"""

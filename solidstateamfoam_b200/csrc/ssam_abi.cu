@@ -1799,6 +1799,27 @@ static ssam_status mixtureFaceVisc(ssam_ctx* ctx, const ssam_mixture_params* p, 
     ctx->faceFieldSet[ff] = true;
     return finish(ctx);
 }
+ssam_status ssam_face_interpolate(ssam_ctx* ctx, int field, int ff) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    CHECK(field >= 0 && field < SSAM_F_COUNT && ncompOf(field) == 1, SSAM_ERR_INVALID, "scalar field id expected");
+    CHECK(ff >= 0 && ff < SSAM_FF_COUNT, SSAM_ERR_INVALID, "bad face field id");
+    TRY(need(ctx, field, "field to interpolate"));
+    TRY(ensureFaceField(ctx, ff));
+    FaceViscArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nCells = ctx->nCells;
+    a.nIF = ctx->nIF;
+    a.nBnd = ctx->nBnd;
+    a.geo = ctx->geo;
+    a.owner = ctx->owner;
+    a.neighbour = ctx->neighbour;
+    a.bndFlags = ctx->bndFlags;
+    a.alpha = ctx->plane[field][0];
+    a.out = ctx->faceField[ff];
+    LAUNCH(k_face_interpolate, gridFor(ctx->nFaces, 256), 256, a);
+    ctx->faceFieldSet[ff] = true;
+    return finish(ctx);
+}
 ssam_status ssam_mixture_muf(ssam_ctx* ctx, const ssam_mixture_params* p) { return mixtureFaceVisc(ctx, p, false); }
 ssam_status ssam_mixture_nuf(ssam_ctx* ctx, const ssam_mixture_params* p) { return mixtureFaceVisc(ctx, p, true); }
 

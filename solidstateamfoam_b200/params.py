@@ -14,7 +14,7 @@ BC_VALUE, BC_ZERO_GRADIENT = 0, 1
 F_PRGH, F_Z, F_SIGMAF_PP, F_DEPSEQ, F_EPSEQ, F_SIGMAVM = range(20, 26)
 F_GRADALPHA, F_CURVATURE = 26, 27
 F_COUNT = 28
-FF_NHATF, FF_MUF, FF_NUF = range(3)
+FF_NHATF, FF_MUF, FF_NUF, FF_KF = range(4)
 FIELD_NAMES = ["U", "temp", "alpha1", "p", "epsilonDotEq", "nu1", "nu2", "sigmaf", "sigmay", "nu", "muEff", "rho",
                "cp", "k", "qvisc", "qfric", "gradU", "strainRate", "rhoSolver", "rhoCp", "p_rgh", "Z", "sigmafPP",
                "dEpsilonEq", "epsilonEq", "sigmavm", "gradAlpha", "interfaceProperties:K"]

@@ -347,6 +347,10 @@ def test_muf_nuf_face_fields(ctx, name):
         got = ctx.face_field(ff, m.nInternalFaces, m.nBoundaryFaces)
         assert np.array_equal(got, ref)
         assert np.isfinite(ref).all() and (ref > 0).all()
+    # kf = thermo.k() on the faces (fvm::laplacian(kf, temp), fluid/TEqn.H:22): linear interpolation, bit-exact
+    ctx.upload(P.F_K, oc.internal(P.F_K), oc.boundary(P.F_K))
+    ctx.face_interpolate(P.F_K, P.FF_KF)
+    assert np.array_equal(ctx.face_field(P.FF_KF, m.nInternalFaces, m.nBoundaryFaces), oc.face_interpolate(P.F_K))
     with pytest.raises(capi.SsamError):
         ctx.face_field(7, 1, 1)
 

@@ -137,3 +137,4 @@ def test_muf_nuf_closed_form():
     assert np.allclose(muf, mu_ref, rtol=1e-13)
     assert np.allclose(nuf, mu_ref / (la * mix.rho1 + (1 - la) * mix.rho2), rtol=1e-13)
     assert O.field_min_max([oc], P.F_NU1) == (n1.min(), n1.max())
+    assert np.allclose(oc.face_interpolate(P.F_NU1), face(n1), rtol=1e-14)  # fvc::interpolate, linear
