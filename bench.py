@@ -300,7 +300,7 @@ def run_gpu(args):
     gi, gb = ctx.download(P.F_U)  # U with the tool-patch BC applied, as the solver would hold it
     ref_out_i, _ = ctx.download(case.outputs[0])
     layout_dev = "tile-compact" if ctx.layout_is_compact() else "caller order"
-    if n_ranks == 1 and ctx.layout_is_compact():
+    if n_ranks == 1 and ctx.layout_is_compact() and os.environ.get("SSAM_E2E_SAME_CONTEXT") is None:
         # host-staged mode: PCIe dominates and the chunk pipeline needs contiguous cell ranges, so a caller that
         # keeps its fields on the host selects the caller-order layout (ssam_set_cell_layout) -- second context
         ctx_h = capi.Context(local)

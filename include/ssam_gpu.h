@@ -206,7 +206,7 @@ SSAM_API ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant);
  * brick of the mesh.  ssam_field_upload/download and ssam_update_fused_host apply the permutation, every
  * addressing table above stays in the caller's numbering, per-cell face order (and so every result bit) is
  * unchanged; only ssam_field_device_ptr exposes the device order (SSAM_ADDR_CELL_ORDER tells which cell is where).
- * The chunk-pipelined ssam_update_fused_host needs SSAM_LAYOUT_CALLER (it falls back to unpipelined otherwise). */
+ * ssam_update_fused_host is chunk-pipelined in both layouts; it overlaps best with SSAM_LAYOUT_CALLER. */
 enum { SSAM_LAYOUT_CALLER = 0, SSAM_LAYOUT_AUTO = 1, SSAM_LAYOUT_COMPACT = 2 };
 SSAM_API ssam_status ssam_set_cell_layout(ssam_ctx* ctx, int mode);
 /* Host-only helper (no context, no GPU): the tile-compact order ssam_mesh_set would compute for this mesh

@@ -55,6 +55,10 @@ struct ssam_ctx {
     int* perm = nullptr;      // device position i holds the caller's cell perm[i] (nullptr = identity)
     int* faceKey = nullptr;   // internal faces: index of the face in the caller's mesh (permuted layout only)
     std::vector<int> permHost;
+    int* invPerm = nullptr;             // caller cell -> device position (permuted layout only)
+    std::vector<int> tileMaxCallerCell;  // per tile, for the host-staged pipeline (built on first use)
+    std::vector<int> pipeWaitIn, pipeOutWait;  // chunk dependencies of that pipeline, cached per chunk count
+    int pipeChunks = 0;
     int *origOwner = nullptr, *origNeighbour = nullptr;  // the caller's owner / neighbour (permuted layout only)
     ssam_ctx* refAddr = nullptr;  // addressing tables in the caller's numbering, built on demand
     double remotePerCellCaller = 0.0, remotePerCellCompact = 0.0;
@@ -234,6 +238,9 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->descCoupled);
     devFree(c->descOrder);
     devFree(c->perm);
+    devFree(c->invPerm);
+    c->tileMaxCallerCell.clear();
+    c->pipeChunks = 0;
     devFree(c->faceKey);
     devFree(c->origOwner);
     devFree(c->origNeighbour);
@@ -1322,6 +1329,9 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
         // from here on uploads / downloads of cell values go through the permutation
         TRY(devAlloc(ctx, &ctx->perm, nC));
         CU(cudaMemcpyAsync(ctx->perm, pm.perm.data(), nC * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(devAlloc(ctx, &ctx->invPerm, nC));
+        CU(cudaMemcpyAsync(ctx->invPerm, pm.inv.data(), nC * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
         ctx->permHost.swap(pm.perm);
     }
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1904,6 +1914,7 @@ ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* 
 struct ChunkPlan {
     int nChunks = 0, tilesPerChunk = 0;
     std::vector<cudaEvent_t> evIn, evOut;
+    std::vector<int> waitIn;  // compute chunk k may start after upload chunk waitIn[k] (empty: k+1)
 };
 
 static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, int flags,
@@ -2015,7 +2026,8 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         if (plan) {
             for (int k = 0; k < plan->nChunks; ++k) {
                 const int t0 = k * plan->tilesPerChunk, t1 = std::min(ctx->nTiles, t0 + plan->tilesPerChunk);
-                CU(cudaStreamWaitEvent(ctx->stream, plan->evIn[std::min(k + 1, plan->nChunks - 1)], 0));
+                const int dep = plan->waitIn.empty() ? std::min(k + 1, plan->nChunks - 1) : plan->waitIn[size_t(k)];
+                CU(cudaStreamWaitEvent(ctx->stream, plan->evIn[size_t(dep)], 0));
                 TRY(launchCellsTiled(ctx, a, model1, ctx->tileIota + t0, t1 - t0, ctx->stream));
                 CU(cudaEventRecord(plan->evOut[k], ctx->stream));
             }
@@ -2101,7 +2113,51 @@ static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_par
     for (int i = 0; i < 4; ++i)
         if (hi[i]) TRY(ensureField(ctx, fIn[i]));
     const size_t chunkCells = size_t(plan.tilesPerChunk) * TILE;
-    TRY(ensureStage(ctx, std::max(size_t(ctx->nBnd) * 3, 2 * chunkCells * 3)));
+    const bool permuted = ctx->perm != nullptr;
+    std::vector<int> outWait;  // download chunk j may start after compute chunk outWait[j]
+    int nScalarIn = 0;
+    for (int i = 1; i < 4; ++i) nScalarIn += hi[i] ? 1 : 0;
+    if (permuted) {
+        // tile-compact layout: the caller's chunk [c0, c1) is scattered over the device order.  Compute chunk k needs
+        // every caller cell its tiles (and their neighbours) hold; download chunk j needs every tile that holds
+        // one of its cells.  Both are monotone enough for a pipeline because runs of 64 caller cells stay together
+        // and clusters only reach a few mesh layers.
+        if (ctx->tileMaxCallerCell.empty()) {
+            int* d = nullptr;
+            TRY(devAlloc(ctx, &d, size_t(ctx->nTiles)));
+            k_tile_max_caller_cell<<<ctx->nTiles, 128, 0, ctx->stream>>>(ctx->ownerStart, ctx->neighbour, ctx->extraStart,
+                                                                       ctx->extra, ctx->perm, ctx->nCells, ctx->nIF,
+                                                                       ctx->nTiles, d);
+            ctx->launches++;
+            ctx->tileMaxCallerCell.resize(size_t(ctx->nTiles));
+            CU(cudaMemcpyAsync(ctx->tileMaxCallerCell.data(), d, size_t(ctx->nTiles) * sizeof(int), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(d);
+        }
+        if (ctx->pipeChunks != nChunks) {
+            ctx->pipeWaitIn.assign(size_t(nChunks), nChunks - 1);
+            for (int k = 0; k < nChunks; ++k) {
+                int m = 0;
+                for (int t = k * plan.tilesPerChunk; t < std::min(ctx->nTiles, (k + 1) * plan.tilesPerChunk); ++t)
+                    m = std::max(m, ctx->tileMaxCallerCell[size_t(t)]);
+                ctx->pipeWaitIn[size_t(k)] = std::min(nChunks - 1, int(size_t(m) / chunkCells));
+            }
+            ctx->pipeOutWait.assign(size_t(nChunks), 0);
+            for (int i = 0; i < ctx->nCells; ++i) {
+                const size_t j = size_t(ctx->permHost[size_t(i)]) / chunkCells;
+                ctx->pipeOutWait[j] = std::max(ctx->pipeOutWait[j], (i / TILE) / plan.tilesPerChunk);
+            }
+            ctx->pipeChunks = nChunks;
+        }
+        plan.waitIn = ctx->pipeWaitIn;
+        outWait = ctx->pipeOutWait;
+    }
+    // staging: uploads 2 x (3 + scalars) x chunk, downloads 2 x nOut x chunk (permuted layout only)
+    const size_t upStage = 2 * chunkCells * size_t(3 + (permuted ? nScalarIn : 0));
+    const size_t dnStage = permuted ? 2 * chunkCells * size_t(std::max(io->nOut, 1)) : 0;
+    TRY(ensureStage(ctx, std::max(size_t(ctx->nBnd) * 3, upStage + dnStage)));
+    double* const dnBase = ctx->stage + upStage;
     // order the copy streams after whatever the caller queued on the compute stream
     CU(cudaEventRecord(evStart, ctx->stream));
     CU(cudaStreamWaitEvent(ctx->h2dStream, evStart, 0));
@@ -2120,15 +2176,30 @@ static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_par
         const int c1 = int(std::min(size_t(ctx->nCells), size_t(k + 1) * chunkCells));
         const int n = c1 - c0;
         if (n > 0) {
-            double* stg = ctx->stage + size_t(k & 1) * chunkCells * 3;
+            double* stg = ctx->stage + size_t(k & 1) * (upStage / 2);
             cudaMemcpyAsync(stg, io->U_i + size_t(c0) * 3, size_t(n) * 3 * sizeof(double), cudaMemcpyHostToDevice,
                             ctx->h2dStream);
-            k_aos_to_soa_n<<<gridFor((long long)n * 3, 256), 256, 0, ctx->h2dStream>>>(stg, n, 3, plU, c0, nullptr);
-            ctx->launches++;
-            for (int i = 1; i < 4; ++i)
-                if (hi[i])
-                    cudaMemcpyAsync(ctx->plane[fIn[i]][0] + c0, hi[i] + c0, size_t(n) * sizeof(double),
-                                    cudaMemcpyHostToDevice, ctx->h2dStream);
+            if (permuted) {
+                k_chunk_scatter<<<gridFor((long long)n * 3, 256), 256, 0, ctx->h2dStream>>>(stg, n, 3, plU, c0, ctx->invPerm);
+                ctx->launches++;
+                int slot = 0;
+                for (int i = 1; i < 4; ++i) {
+                    if (!hi[i]) continue;
+                    double* ss = stg + chunkCells * size_t(3 + slot++);
+                    cudaMemcpyAsync(ss, hi[i] + c0, size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->h2dStream);
+                    PlanePtrs p1;
+                    for (int q = 0; q < 16; ++q) p1.p[q] = q == 0 ? ctx->plane[fIn[i]][0] : nullptr;
+                    k_chunk_scatter<<<gridFor(n, 256), 256, 0, ctx->h2dStream>>>(ss, n, 1, p1, c0, ctx->invPerm);
+                    ctx->launches++;
+                }
+            } else {
+                k_aos_to_soa_n<<<gridFor((long long)n * 3, 256), 256, 0, ctx->h2dStream>>>(stg, n, 3, plU, c0, nullptr);
+                ctx->launches++;
+                for (int i = 1; i < 4; ++i)
+                    if (hi[i])
+                        cudaMemcpyAsync(ctx->plane[fIn[i]][0] + c0, hi[i] + c0, size_t(n) * sizeof(double),
+                                        cudaMemcpyHostToDevice, ctx->h2dStream);
+            }
         }
         if (cudaEventRecord(plan.evIn[k], ctx->h2dStream) != cudaSuccess) st = SSAM_ERR_CUDA;
     }
@@ -2146,22 +2217,39 @@ static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_par
         const int c0 = int(std::min(size_t(ctx->nCells), size_t(k) * chunkCells));
         const int c1 = int(std::min(size_t(ctx->nCells), size_t(k + 1) * chunkCells));
         if (c1 <= c0) continue;
-        CU(cudaStreamWaitEvent(ctx->d2hStream, plan.evOut[k], 0));
+        CU(cudaStreamWaitEvent(ctx->d2hStream, plan.evOut[size_t(permuted ? outWait[size_t(k)] : k)], 0));
         for (int o = 0; o < io->nOut; ++o) {
             const int f = io->outFields[o];
             if (f == SSAM_F_QFRIC || !(io->out_i && io->out_i[o])) continue;
             TRY(need(ctx, f, "requested output was not produced by this update"));
-            CU(cudaMemcpyAsync(io->out_i[o] + c0, ctx->plane[f][0] + c0, size_t(c1 - c0) * sizeof(double),
-                               cudaMemcpyDeviceToHost, ctx->d2hStream));
+            const double* src = ctx->plane[f][0] + c0;
+            if (permuted) {
+                double* g = dnBase + (size_t(k & 1) * size_t(io->nOut) + size_t(o)) * chunkCells;
+                k_chunk_gather<<<gridFor(c1 - c0, 256), 256, 0, ctx->d2hStream>>>(g, c1 - c0, ctx->plane[f][0], c0,
+                                                                                 ctx->invPerm);
+                ctx->launches++;
+                src = g;
+            }
+            CU(cudaMemcpyAsync(io->out_i[o] + c0, src, size_t(c1 - c0) * sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx->d2hStream));
         }
     }
     CU(cudaStreamWaitEvent(ctx->d2hStream, evTail, 0));
     for (int o = 0; o < io->nOut; ++o) {
         const int f = io->outFields[o];
         TRY(need(ctx, f, "requested output was not produced by this update"));
-        if (f == SSAM_F_QFRIC && io->out_i && io->out_i[o])
-            CU(cudaMemcpyAsync(io->out_i[o], ctx->plane[f][0], size_t(ctx->nCells) * sizeof(double),
-                               cudaMemcpyDeviceToHost, ctx->d2hStream));
+        if (f == SSAM_F_QFRIC && io->out_i && io->out_i[o]) {
+            if (permuted) {
+                cudaStream_t keep2 = ctx->stream;
+                ctx->stream = ctx->d2hStream;  // downloadAoS applies the permutation (and synchronises its stream)
+                const ssam_status s2 = downloadAoS(ctx, io->out_i[o], ctx->nCells, 1, ctx->plane[f], 0);
+                ctx->stream = keep2;
+                if (s2 != SSAM_OK) return s2;
+            } else {
+                CU(cudaMemcpyAsync(io->out_i[o], ctx->plane[f][0], size_t(ctx->nCells) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ctx->d2hStream));
+            }
+        }
         if (io->out_b && io->out_b[o] && ctx->nBnd)
             CU(cudaMemcpyAsync(io->out_b[o], ctx->plane[f][0] + ctx->nCells, size_t(ctx->nBnd) * sizeof(double),
                                cudaMemcpyDeviceToHost, ctx->d2hStream));
@@ -2189,8 +2277,7 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
     // itself and its two neighbours)
     int nChunks = ctx->hostChunks >= 0 ? std::min(ctx->hostChunks, 64) : std::min(16, ctx->nTiles / 1024);
     while (nChunks > 1 && (ctx->nTiles + nChunks - 1) / nChunks < ctx->bandwidthTiles + 1) --nChunks;
-    // (the pipeline moves contiguous cell ranges, which only exist in the caller's cell order)
-    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel == 1 && ctx->nTilesOversize == 0 && !ctx->perm)
+    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel == 1 && ctx->nTilesOversize == 0)
         return updateFusedHostPipelined(ctx, p, io, nChunks);
     return updateFusedHostSimple(ctx, p, io);
 }

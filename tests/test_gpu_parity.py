@@ -217,11 +217,19 @@ def test_edge_values(ctx):
     assert np.isnan(ki[6]) and np.isnan(oc.field(P.F_K)[6])
 
 
+@pytest.mark.parametrize("layout", [P.LAYOUT_CALLER, P.LAYOUT_COMPACT], ids=["caller", "compact"])
 @pytest.mark.parametrize("chunks", [0, 3, 7])
-def test_host_staged_update_equals_device_resident(ctx, chunks):
-    """ssam_update_fused_host (the e2e path): plain and pipelined over chunks, bit-identical to the
-    device-resident update on the same inputs"""
+def test_host_staged_update_equals_device_resident(chunks, layout):
+    """ssam_update_fused_host (the e2e path): plain and pipelined over chunks, in both cell layouts, bit-identical
+    to the device-resident update on the same inputs"""
     case = cases.cfg2(dims=(64, 32, 24))  # 192 tiles, bandwidth 8 tiles
+    with capi.Context(0) as ctx:
+        ctx.set_cell_layout(layout)
+        _host_staged_check(ctx, case, chunks)
+        assert ctx.layout_is_compact() == (layout == P.LAYOUT_COMPACT)
+
+
+def _host_staged_check(ctx, case, chunks):
     ctx.load_case(case)
     ctx.update_fused(case.params, 0)
     ref = {f: ctx.download(f) for f in case.outputs}
