@@ -112,7 +112,10 @@ enum {
      * immiscibleIncompressibleTwoPhaseThermalMixture.H:80, consumed by alphaEqn.H:154 and UEqn.H:31) */
     SSAM_F_GRADALPHA = 26,  /* vector, fvc::grad(alpha1, "nHat")                                    */
     SSAM_F_CURVATURE = 27,  /* interfaceProperties::K_ = -fvc::div(nHatf_)                          */
-    SSAM_F_COUNT = 28
+    /* explicit part of turbulence.divDevRhoReff(rho, U) (fluid/UEqn.H:13; OpenFOAM linearViscousStress):
+     * -fvc::div((rho*nuEff)*dev2(T(fvc::grad(U)))), laminar nuEff = thermo.nu()                      */
+    SSAM_F_DIVDEVRHOREFF = 28, /* vector                                                              */
+    SSAM_F_COUNT = 29
 };
 
 /* ---- model parameters (what the reference reads from dictionaries) ---------- */
@@ -295,6 +298,13 @@ SSAM_API ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3],
  * OpenFOAM): another fvc::grad(U) -> GRADU, then Z, SIGMAF_PP, DEPSEQ, EPSEQ += DEPSEQ, SIGMAVM.
  * Reads U, EPSDOT, T, MUEFF, PRGH, EPSEQ. */
 SSAM_API ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p);
+
+/* Explicit part of the momentum equation's viscous term (fluid/UEqn.H:13 `turbulence.divDevRhoReff(rho, U)`, for
+ * the laminar model OpenFOAM's linearViscousStress::divDevRhoReff):
+ *   DIVDEVRHOREFF = -fvc::div((rho*nuEff)*dev2(T(fvc::grad(U))))     with rho = RHO_SOLVER, nuEff = NU
+ * (Gauss linear; the implicit -fvm::laplacian(rho*nuEff, U) stays in OpenFOAM).  Reads GRADU (ssam_grad_u or the
+ * fused update with flag 1), RHO_SOLVER, NU incl. their boundary values. */
+SSAM_API ssam_status ssam_div_dev_rho_reff_explicit(ssam_ctx* ctx);
 
 /* interfaceProperties::correct() = calculateK(), the other half of thermo.correct()
  * (immiscibleIncompressibleTwoPhaseThermalMixture.H:77-81).  The class itself is OpenFOAM v1806 library code

@@ -65,7 +65,8 @@ struct Case {
 };
 
 int ncompOf(int field) {
-    return (field == SSAM_F_U || field == SSAM_F_GRADALPHA) ? 3 : (field == SSAM_F_GRADU ? 9 : 1);
+    return (field == SSAM_F_U || field == SSAM_F_GRADALPHA || field == SSAM_F_DIVDEVRHOREFF) ? 3
+                                                                                            : (field == SSAM_F_GRADU ? 9 : 1);
 }
 
 Fld& fieldRef(Case& c, int field) {
@@ -947,6 +948,75 @@ int interfaceCorrect(Case& c, double deltaN, int stage) {
     return 0;
 }
 
+// ================================================================================================
+// Explicit part of turbulence.divDevRhoReff(rho, U) (fluid/UEqn.H:13).  OpenFOAM v1806 library code
+// (linearViscousStress<BasicTurbulenceModel>::divDevRhoReff), restated -- PARITY UNPINNED:
+//     - fvc::div((alpha*rho*nuEff())*dev2(T(fvc::grad(U))))        [- fvm::laplacian(...) stays in OpenFOAM]
+// alpha = 1, nuEff = nu (laminar), fvc::div(vf) = surfaceIntegrate(Sf & interpolate(vf)), linear interpolation.
+// dev2(t) = t - twoThirdsI*tr(t); Vector & Tensor = (v.x*t.xx + v.y*t.yx + v.z*t.zx, ...).
+// ================================================================================================
+int divDevRhoReffExplicit(Case& c) {
+    if (!c.set[SSAM_F_GRADU] || !c.set[SSAM_F_RHO_SOLVER] || !c.set[SSAM_F_NU]) {
+        c.err = "gradU / rho / nu not set";
+        return SSAM_ERR_MISSING_FIELD;
+    }
+    const Fld& G = c.f[SSAM_F_GRADU];
+    const Fld coeff = mulFF(c.f[SSAM_F_RHO_SOLVER], c.f[SSAM_F_NU]);  // rho*nuEff
+    Fld X(size_t(c.nTot) * 9);
+    for (int32_t i = 0; i < c.nTot; ++i) {
+        const double* g = &G[size_t(i) * 9];
+        const double t[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};  // T(gradU)
+        const double ii = (2.0 / 3.0) * (t[0] + t[4] + t[8]);                        // twoThirdsI*tr(t)
+        double d[9];
+        for (int k = 0; k < 9; ++k) d[k] = t[k];
+        d[0] = t[0] - ii; d[4] = t[4] - ii; d[8] = t[8] - ii;                         // dev2
+        for (int k = 0; k < 9; ++k) X[size_t(i) * 9 + k] = coeff[i] * d[k];
+    }
+    // Sf & interpolate(X) per face, surfaceIntegrate, negate
+    Fld& R = fieldRef(c, SSAM_F_DIVDEVRHOREFF);
+    std::fill(R.begin(), R.end(), 0.0);
+    auto flux = [&](const double* xf, int32_t f, double* out) {
+        const double* S = &c.Sf[3 * size_t(f)];
+        for (int j = 0; j < 3; ++j) out[j] = S[0] * xf[j] + S[1] * xf[3 + j] + S[2] * xf[6 + j];
+    };
+    Fld phi(size_t(c.nFaces) * 3);
+    for (int32_t f = 0; f < c.nIF; ++f) {
+        const double* xP = &X[size_t(c.owner[f]) * 9];
+        const double* xN = &X[size_t(c.neighbour[f]) * 9];
+        double xf[9];
+        for (int k = 0; k < 9; ++k) xf[k] = c.w[f] * (xP[k] - xN[k]) + xN[k];
+        flux(xf, f, &phi[size_t(f) * 3]);
+    }
+    for (int p = 0; p < c.nPatches; ++p)
+        for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) {
+            const double* xb = &X[size_t(c.nCells + f - c.nIF) * 9];
+            double xf[9];
+            if (c.patchKind[p] == SSAM_PATCH_PROCESSOR) {
+                const double* xP = &X[size_t(c.owner[f]) * 9];
+                for (int k = 0; k < 9; ++k) xf[k] = c.w[f] * xP[k] + (1.0 - c.w[f]) * xb[k];
+            } else {
+                for (int k = 0; k < 9; ++k) xf[k] = xb[k];
+            }
+            flux(xf, f, &phi[size_t(f) * 3]);
+        }
+    for (int32_t f = 0; f < c.nIF; ++f)
+        for (int j = 0; j < 3; ++j) {
+            R[size_t(c.owner[f]) * 3 + j] += phi[size_t(f) * 3 + j];
+            R[size_t(c.neighbour[f]) * 3 + j] -= phi[size_t(f) * 3 + j];
+        }
+    for (int32_t f = c.nIF; f < c.nFaces; ++f)
+        for (int j = 0; j < 3; ++j) R[size_t(c.owner[f]) * 3 + j] += phi[size_t(f) * 3 + j];
+    for (int32_t cc = 0; cc < c.nCells; ++cc)
+        for (int j = 0; j < 3; ++j) R[size_t(cc) * 3 + j] = -(R[size_t(cc) * 3 + j] / c.V[cc]);
+    for (int p = 0; p < c.nPatches; ++p) {
+        if (c.patchKind[p] == SSAM_PATCH_PROCESSOR) continue;  // neighbour rank's cell value, by halo
+        for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f)
+            for (int j = 0; j < 3; ++j) R[size_t(c.nCells + f - c.nIF) * 3 + j] = R[size_t(c.owner[f]) * 3 + j];
+    }
+    c.set[SSAM_F_DIVDEVRHOREFF] = true;
+    return 0;
+}
+
 // interfaceProperties constructor: deltaN_ = 1e-8/pow(average(alpha1.mesh().V()), 1.0/3.0)
 double interfaceDeltaN(const std::vector<const Case*>& ranks) {
     double sum = 0;
@@ -1213,6 +1283,7 @@ void orc_field_min_max(orc_case** cases, int nRanks, int field, double* mn, doub
     *mn = lo;
     *mx = hi;
 }
+int orc_div_dev_rho_reff_explicit(orc_case* h) { return divDevRhoReffExplicit(CASE(h)); }
 int orc_interface_correct(orc_case* h, double deltaN, int stage) { return interfaceCorrect(CASE(h), deltaN, stage); }
 double* orc_interface_nhatf(orc_case* h) { return CASE(h).nHatf.data(); }
 double orc_interface_delta_n(orc_case** cases, int nRanks) {

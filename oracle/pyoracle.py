@@ -51,6 +51,7 @@ def lib():
         L.orc_face_field.restype = dp
         L.orc_face_field.argtypes = [vp, C.c_int]
         L.orc_field_min_max.argtypes = [C.POINTER(vp), C.c_int, C.c_int, dp, dp]
+        L.orc_div_dev_rho_reff_explicit.argtypes = [vp]
         L.orc_interface_correct.argtypes = [vp, C.c_double, C.c_int]
         L.orc_interface_nhatf.restype = dp
         L.orc_interface_nhatf.argtypes = [vp]
@@ -147,6 +148,10 @@ class OracleCase:
 
     def stress_strain(self, p, form=FAITHFUL):
         self._chk(lib().orc_stress_strain(self.h, C.byref(p), form))
+
+    def div_dev_rho_reff_explicit(self):
+        """-fvc::div((rho*nuEff)*dev2(T(grad U))) from GRADU, RHO_SOLVER, NU"""
+        self._chk(lib().orc_div_dev_rho_reff_explicit(self.h))
 
     def interface_correct(self, deltaN, stage=3):
         """interfaceProperties::correct(); stage 1 = cell gradient, 2 = the rest (halo steps go in between)."""

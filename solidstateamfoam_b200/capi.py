@@ -22,7 +22,7 @@ SYMBOLS = [
     "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
-    "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_interface_correct",
+    "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_div_dev_rho_reff_explicit", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
     "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange", "ssam_halo_transport",
@@ -85,6 +85,7 @@ def load():
         getattr(L, "ssam_mixture_" + n).argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_solver_rho_rhocp.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_stress_strain.argtypes = [vp, C.POINTER(P.StressStrainParams)]
+    L.ssam_div_dev_rho_reff_explicit.argtypes = [vp]
     L.ssam_interface_correct.argtypes = [vp, C.c_double, C.c_uint32]
     L.ssam_interface_nhatf_download.argtypes = [vp, dp, dp]
     L.ssam_interface_nhatf_device_ptr.restype = C.c_void_p
@@ -279,6 +280,10 @@ class Context:
 
     def stress_strain(self, p: P.StressStrainParams):
         self._chk(self.L.ssam_stress_strain(self.h, C.byref(p)))
+
+    def div_dev_rho_reff_explicit(self):
+        """-fvc::div((rho*nuEff)*dev2(T(grad U))) -> F_DIVDEVRHOREFF"""
+        self._chk(self.L.ssam_div_dev_rho_reff_explicit(self.h))
 
     def interface_correct(self, deltaN: float, flags: int = 0):
         """interfaceProperties::correct(): GRADALPHA, nHatf, CURVATURE from ALPHA1."""

@@ -117,7 +117,9 @@ namespace {
 
 thread_local std::string g_globalErr;
 
-int ncompOf(int f) { return (f == SSAM_F_U || f == SSAM_F_GRADALPHA) ? 3 : (f == SSAM_F_GRADU ? 9 : 1); }
+int ncompOf(int f) {
+    return (f == SSAM_F_U || f == SSAM_F_GRADALPHA || f == SSAM_F_DIVDEVRHOREFF) ? 3 : (f == SSAM_F_GRADU ? 9 : 1);
+}
 
 ssam_status fail(ssam_ctx* c, ssam_status st, const std::string& msg) {
     if (c)
@@ -1687,6 +1689,37 @@ ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p
     s.accumulate = accumulate ? 1 : 0;
     LAUNCH((k_map<StressStrainStage>), mapGrid(ctx), 256, ctx->nTot, s);
     for (int f : outs) ctx->isSet[f] = true;
+    return finish(ctx);
+}
+
+// explicit part of turbulence.divDevRhoReff(rho, U)  (fluid/UEqn.H:13)
+ssam_status ssam_div_dev_rho_reff_explicit(ssam_ctx* ctx) {
+    CHECK(ctx, SSAM_ERR_INVALID, "null context");
+    TRY(need(ctx, SSAM_F_GRADU, "gradU (ssam_grad_u, or ssam_update_fused with flag 1)"));
+    TRY(need(ctx, SSAM_F_RHO_SOLVER, "rho (ssam_solver_rho_rhocp)"));
+    TRY(need(ctx, SSAM_F_NU, "nu (thermo.correct())"));
+    TRY(ensureField(ctx, SSAM_F_DIVDEVRHOREFF));
+    if (ctx->nProcPatches) {  // boundary values of the operands on processor patches = neighbour cell values
+        const int ops[3] = {SSAM_F_GRADU, SSAM_F_RHO_SOLVER, SSAM_F_NU};
+        TRY(haloExchangeFields(ctx, ops, 3, ctx->stream));
+    }
+    DivDevArgs a;
+    a.nCells = ctx->nCells;
+    a.nIF = ctx->nIF;
+    a.nBnd = ctx->nBnd;
+    a.geo = ctx->geo;
+    a.neighbour = ctx->neighbour;
+    a.ownerStart = ctx->ownerStart;
+    a.extraStart = ctx->extraStart;
+    a.extra = ctx->extra;
+    a.V = ctx->V;
+    for (int k = 0; k < 9; ++k) a.g[k] = ctx->plane[SSAM_F_GRADU][k];
+    a.rho = ctx->plane[SSAM_F_RHO_SOLVER][0];
+    a.nu = ctx->plane[SSAM_F_NU][0];
+    for (int k = 0; k < 3; ++k) a.out[k] = ctx->plane[SSAM_F_DIVDEVRHOREFF][k];
+    LAUNCH(k_div_dev_cells, gridFor(ctx->nCells, 128), 128, a);
+    if (ctx->nProcPatches) TRY(haloExchangeField(ctx, SSAM_F_DIVDEVRHOREFF));
+    ctx->isSet[SSAM_F_DIVDEVRHOREFF] = true;
     return finish(ctx);
 }
 

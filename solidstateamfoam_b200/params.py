@@ -12,16 +12,16 @@ BC_VALUE, BC_ZERO_GRADIENT = 0, 1
 (F_U, F_T, F_ALPHA1, F_P, F_EPSDOT, F_NU1, F_NU2, F_SIGMAF, F_SIGMAY, F_NU, F_MUEFF, F_RHO, F_CP, F_K, F_QVISC,
  F_QFRIC, F_GRADU, F_STRAINRATE, F_RHO_SOLVER, F_RHOCP) = range(20)
 F_PRGH, F_Z, F_SIGMAF_PP, F_DEPSEQ, F_EPSEQ, F_SIGMAVM = range(20, 26)
-F_GRADALPHA, F_CURVATURE = 26, 27
-F_COUNT = 28
+F_GRADALPHA, F_CURVATURE, F_DIVDEVRHOREFF = 26, 27, 28
+F_COUNT = 29
 FF_NHATF, FF_MUF, FF_NUF, FF_KF = range(4)
 FIELD_NAMES = ["U", "temp", "alpha1", "p", "epsilonDotEq", "nu1", "nu2", "sigmaf", "sigmay", "nu", "muEff", "rho",
                "cp", "k", "qvisc", "qfric", "gradU", "strainRate", "rhoSolver", "rhoCp", "p_rgh", "Z", "sigmafPP",
-               "dEpsilonEq", "epsilonEq", "sigmavm", "gradAlpha", "interfaceProperties:K"]
+               "dEpsilonEq", "epsilonEq", "sigmavm", "gradAlpha", "interfaceProperties:K", "divDevRhoReffExplicit"]
 
 
 def ncomp(field: int) -> int:
-    return 3 if field in (F_U, F_GRADALPHA) else (9 if field == F_GRADU else 1)
+    return 3 if field in (F_U, F_GRADALPHA, F_DIVDEVRHOREFF) else (9 if field == F_GRADU else 1)
 
 
 VISC_NEWTONIAN, VISC_SHEPPARD_WRIGHT, VISC_FKS, VISC_NORTON_HOFF = range(4)

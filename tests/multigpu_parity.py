@@ -119,6 +119,20 @@ def main():
         gi, gb = ctx.download(f)
         check_field(f"rank{rank} {P.FIELD_NAMES[f]}", np.concatenate([gi, gb]), oc.field(f), True)
     assert np.array_equal(ctx.nhatf(case.mesh.nInternalFaces, case.mesh.nBoundaryFaces), oc.nhatf())
+    # explicit viscous-stress divergence across ranks (halos of gradU, rho, nu and of the result)
+    ctx.update_fused(case.params, capi.FUSED_HALO_INPUTS | capi.FUSED_WRITE_GRAD)
+    ctx.solver_rho_rhocp(case.params.mix)
+    for o in ocs:
+        o.solver_rho_rhocp(parts[0].params.mix)
+    ctx.upload(P.F_NU, oc.internal(P.F_NU), oc.boundary(P.F_NU))
+    for f in (P.F_GRADU, P.F_RHO_SOLVER, P.F_NU):
+        O.halo_exchange(ocs, f)
+    for o in ocs:
+        o.div_dev_rho_reff_explicit()
+    O.halo_exchange(ocs, P.F_DIVDEVRHOREFF)
+    ctx.div_dev_rho_reff_explicit()
+    gi, gb = ctx.download(P.F_DIVDEVRHOREFF)
+    check_field(f"rank{rank} divDevRhoReff", np.concatenate([gi, gb]), oc.field(P.F_DIVDEVRHOREFF), True)
     # muf()/nuf() on processor faces, and the cross-rank "Min/max T"
     for f in (P.F_NU1, P.F_NU2):
         ctx.upload(f, oc.internal(f), oc.boundary(f))

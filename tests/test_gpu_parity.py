@@ -473,3 +473,20 @@ def test_tile_compact_layout_is_bit_identical(name):
     for k in a:
         same = (a[k] == b[k]) | ((a[k] != a[k]) & (b[k] != b[k]))
         assert same.all(), f"{k}: {np.count_nonzero(~same)} values differ between the two layouts"
+
+
+@pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly"])
+def test_div_dev_rho_reff_explicit(ctx, name):
+    """-fvc::div((rho*nuEff)*dev2(T(grad U))) (fluid/UEqn.H:13, explicit part): IEEE-only, bit-exact"""
+    case = small_cases()[name]()
+    ctx.load_case(case)
+    ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+    ctx.solver_rho_rhocp(case.params.mix)
+    oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
+    oc.solver_rho_rhocp(case.params.mix)
+    ctx.upload(P.F_NU, oc.internal(P.F_NU), oc.boundary(P.F_NU))  # identical operands (nu agrees to ~1e-15 only)
+    ctx.div_dev_rho_reff_explicit()
+    oc.div_dev_rho_reff_explicit()
+    gi, gb = ctx.download(P.F_DIVDEVRHOREFF)
+    check_field("divDevRhoReff (explicit)", np.concatenate([gi, gb]), oc.field(P.F_DIVDEVRHOREFF), True)
+    assert np.abs(gi).max() > 0

@@ -138,3 +138,34 @@ def test_muf_nuf_closed_form():
     assert np.allclose(nuf, mu_ref / (la * mix.rho1 + (1 - la) * mix.rho2), rtol=1e-13)
     assert O.field_min_max([oc], P.F_NU1) == (n1.min(), n1.max())
     assert np.allclose(oc.face_interpolate(P.F_NU1), face(n1), rtol=1e-14)  # fvc::interpolate, linear
+
+
+def test_div_dev_rho_reff_explicit_analytic():
+    """-div(mu*dev2(T(grad U))): zero for a linear velocity field, -(2/3 mu, 0, 0) for U = (x^2, 0, 0)"""
+    n = 12
+    m = M.hex_block(n, n, n, length=(1.2, 1.2, 1.2))
+    xc = np.concatenate([m.C, m.Cf[m.nInternalFaces:]])
+    nt = m.nCells + m.nBoundaryFaces
+    rho, nu = 2700.0, 3.0e-3
+    for kind in ("linear", "quadratic"):
+        oc = O.OracleCase(m)
+        if kind == "linear":
+            A = np.array([[0.3, -0.2, 0.1], [0.05, 0.4, -0.3], [0.2, 0.1, -0.7]])
+            U = xc @ A
+        else:
+            U = np.stack([xc[:, 0] ** 2, 0 * xc[:, 0], 0 * xc[:, 0]], axis=1)
+        oc.set(P.F_U, U[: m.nCells], U[m.nCells:])
+        oc.grad_u()
+        oc.set(P.F_RHO_SOLVER, np.full(m.nCells, rho), np.full(m.nBoundaryFaces, rho))
+        oc.set(P.F_NU, np.full(m.nCells, nu), np.full(m.nBoundaryFaces, nu))
+        oc.div_dev_rho_reff_explicit()
+        r = oc.internal(P.F_DIVDEVRHOREFF)
+        i, j, k = np.unravel_index(np.arange(m.nCells), (n, n, n), order="F")
+        inner = (i > 1) & (i < n - 2) & (j > 1) & (j < n - 2) & (k > 1) & (k < n - 2)
+        scale = rho * nu
+        if kind == "linear":
+            assert np.abs(r).max() < 1e-9 * scale  # all cells: the corrected boundary gradient is exact too
+        else:
+            assert np.allclose(r[inner], [-(2.0 / 3.0) * scale, 0.0, 0.0], rtol=1e-9, atol=1e-9 * scale)
+        # boundary values: the adjacent cell's value
+        assert np.array_equal(oc.boundary(P.F_DIVDEVRHOREFF), r[m.owner[m.nInternalFaces:]])
