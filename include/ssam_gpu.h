@@ -256,7 +256,10 @@ SSAM_API ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out,
 /* host AoS -> device SoA (transposed on the device); either pointer may be NULL to skip that part */
 SSAM_API ssam_status ssam_field_upload(ssam_ctx* ctx, int field, const double* internal, const double* boundary);
 SSAM_API ssam_status ssam_field_download(ssam_ctx* ctx, int field, double* internal, double* boundary);
-/* device-resident use: pointer to component plane `comp` (length nCells+nBnd: internal then boundary) */
+/* device-resident use: pointer to component plane `comp` (length nCells+nBnd: internal then boundary).  The
+ * internal part is in the library's cell order: entry i belongs to the caller's cell SSAM_ADDR_CELL_ORDER[i]
+ * (identity with SSAM_LAYOUT_CALLER); the boundary part is always in the caller's boundary-face order.
+ * ssam_face_field_device_ptr likewise holds the internal faces in the library's face order. */
 SSAM_API ssam_status ssam_field_device_ptr(ssam_ctx* ctx, int field, int comp, void** ptr, int64_t* len);
 /* 1 if the field currently holds data (uploaded or computed) */
 SSAM_API int ssam_field_is_set(const ssam_ctx* ctx, int field);
