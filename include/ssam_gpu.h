@@ -247,7 +247,9 @@ enum {
     SSAM_ADDR_FACE_COLOUR = 9,  /* [nInternalFaces] greedy face colouring (scatter variant)                  */
     SSAM_ADDR_CELL_ORDER = 10,  /* [nCells] caller's cell label held at each position of the device planes
                                    (identity unless the tile-compact layout is active, see ssam_set_cell_layout) */
-    SSAM_ADDR_COUNT = 11
+    SSAM_ADDR_FACE_ORDER = 11,  /* [nInternalFaces] caller's face index held at each internal-face position of the device
+                                   face fields (identity unless the tile-compact layout is active)              */
+    SSAM_ADDR_COUNT = 12
 };
 SSAM_API ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n);
 SSAM_API ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t n);
@@ -259,7 +261,7 @@ SSAM_API ssam_status ssam_field_download(ssam_ctx* ctx, int field, double* inter
 /* device-resident use: pointer to component plane `comp` (length nCells+nBnd: internal then boundary).  The
  * internal part is in the library's cell order: entry i belongs to the caller's cell SSAM_ADDR_CELL_ORDER[i]
  * (identity with SSAM_LAYOUT_CALLER); the boundary part is always in the caller's boundary-face order.
- * ssam_face_field_device_ptr likewise holds the internal faces in the library's face order. */
+ * ssam_face_field_device_ptr likewise holds the internal faces in the library's face order (SSAM_ADDR_FACE_ORDER). */
 SSAM_API ssam_status ssam_field_device_ptr(ssam_ctx* ctx, int field, int comp, void** ptr, int64_t* len);
 /* 1 if the field currently holds data (uploaded or computed) */
 SSAM_API int ssam_field_is_set(const ssam_ctx* ctx, int field);

@@ -1445,6 +1445,10 @@ ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n) {
         *n = ctx->nCells;
         return SSAM_OK;
     }
+    if (which == SSAM_ADDR_FACE_ORDER) {
+        *n = ctx->nIF;
+        return SSAM_OK;
+    }
     switch (which) {
         case SSAM_ADDR_OWNER_START:
         case SSAM_ADDR_EXTRA_START:
@@ -1468,6 +1472,15 @@ ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t 
     if (n == 0) return SSAM_OK;
     if (which == SSAM_ADDR_CELL_ORDER) {
         for (int64_t i = 0; i < n; ++i) out[i] = ctx->permHost.empty() ? int32_t(i) : ctx->permHost[size_t(i)];
+        return SSAM_OK;
+    }
+    if (which == SSAM_ADDR_FACE_ORDER) {
+        if (ctx->faceKey) {
+            CU(cudaMemcpyAsync(out, ctx->faceKey, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            for (int64_t i = 0; i < n; ++i) out[i] = int32_t(i);
+        }
         return SSAM_OK;
     }
     if (ctx->perm) {  // tables in the caller's numbering

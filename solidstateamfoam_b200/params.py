@@ -32,10 +32,10 @@ ROTSLIP_CONSTANT, ROTSLIP_EXPONENTIAL = 0, 1
 
 (ADDR_OWNER_START, ADDR_EXTRA_START, ADDR_EXTRA_FACE, ADDR_EXTRA_OTHER, ADDR_CELL_FACES_START, ADDR_CELL_FACES,
  ADDR_HALO_SEND_CELLS, ADDR_HALO_PATCH_OFFSETS, ADDR_FRIC_CELLS, ADDR_FACE_COLOUR) = range(10)
-ADDR_CELL_ORDER = 10
+ADDR_CELL_ORDER, ADDR_FACE_ORDER = 10, 11
 LAYOUT_CALLER, LAYOUT_AUTO, LAYOUT_COMPACT = range(3)
 ADDR_NAMES = ["ownerStart", "extraStart", "extraFace", "extraOther", "cellFacesStart", "cellFaces", "haloSendCells",
-              "haloPatchOffsets", "fricCells", "faceColour", "cellOrder"]
+              "haloPatchOffsets", "fricCells", "faceColour", "cellOrder", "faceOrder"]
 
 UNIQUE_ID_BYTES = 128
 

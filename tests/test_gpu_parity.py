@@ -439,8 +439,19 @@ def test_tile_compact_layout_is_bit_identical(name):
             assert c.layout_is_compact() == (mode == P.LAYOUT_COMPACT)
             order = c.addressing(P.ADDR_CELL_ORDER)
             assert np.array_equal(np.sort(order), np.arange(m.nCells))
+            forder = c.addressing(P.ADDR_FACE_ORDER)
+            assert np.array_equal(np.sort(forder), np.arange(m.nInternalFaces))
             if mode == P.LAYOUT_COMPACT:
                 assert not np.array_equal(order, np.arange(m.nCells))
+                # device faces are grouped by (device position of) the caller's owner, caller order within
+                inv = np.empty(m.nCells, dtype=np.int64)
+                inv[order] = np.arange(m.nCells)
+                own_dev = inv[m.owner[forder]]
+                assert (np.diff(own_dev) >= 0).all()
+                same = np.diff(own_dev) == 0
+                assert (np.diff(forder)[same] > 0).all()
+            else:
+                assert np.array_equal(forder, np.arange(m.nInternalFaces))
             out = {}
             for variant in (0, 1):
                 c.set_cell_kernel(variant)
