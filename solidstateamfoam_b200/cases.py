@@ -142,7 +142,7 @@ def _hex(dims, cell, side=(-1,) * 6, rank=0, origin=(0.0, 0.0, 0.0), affine=M.ID
     return M.hex_block(nx, ny, nz, origin, (nx * cell, ny * cell, nz * cell), grading, affine, side, rank)
 
 
-def cfg1(dims=(64, 64, 32), step=0, affine=M.IDENTITY, grading=(1.0, 1.0, 1.0)) -> Case:
+def cfg1(dims=(64, 64, 32), step=0, affine=M.IDENTITY, grading=(1.0, 1.0, 1.0), visc1=None) -> Case:
     """hex 64x64x32, alpha1 step, SheppardWright AA6061, constantRotationalSlip + constantSlipStick."""
     seed = SEED0 + 1
     m = _hex(dims, 0.5e-3, affine=affine, grading=grading)
@@ -150,16 +150,17 @@ def cfg1(dims=(64, 64, 32), step=0, affine=M.IDENTITY, grading=(1.0, 1.0, 1.0)) 
     mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
     stick = P.constant_slip_stick(top, betaTQ=0.9, delta=0.5, omega=OMEGA, muf=0.3)
     rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
-    return _finish("cfg1", m, _fields(m, seed, "step", step=step), sheppard_wright_aa6061(), mix, stick, rot, seed)
+    return _finish("cfg1", m, _fields(m, seed, "step", step=step), visc1 or sheppard_wright_aa6061(), mix, stick, rot,
+                   seed)
 
 
 def cfg2(dims=(256, 256, 128), units="Kelvin", side=(-1,) * 6, rank=0, origin=(0.0, 0.0, 0.0), z0=None,
-         box=None) -> Case:
+         box=None, visc1=None, k_coeffs=(100.0, 0.2, -1e-4, 1e-8)) -> Case:
     """hex 256x256x128, FKS + cubic k(T) for phase 1 (Kelvin or Celsius fit)."""
     seed = SEED0 + 2 + rank
     m = _hex(dims, 0.25e-3, side=side, rank=rank, origin=origin)
     top = m.patch_id("zmax")
-    k1 = P.k_cubic(100.0, 0.2, -1e-4, 1e-8, 293.0 if units == "Kelvin" else 20.0,
+    k1 = P.k_cubic(*k_coeffs, 293.0 if units == "Kelvin" else 20.0,
                    855.0 if units == "Kelvin" else 582.0, units)
     mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], k1, P.k_constant(AIR["k"]))
     if top >= 0:
@@ -168,8 +169,8 @@ def cfg2(dims=(256, 256, 128), units="Kelvin", side=(-1,) * 6, rank=0, origin=(0
     else:  # interior slab of a decomposed box: no tool patch on this rank
         stick = P.no_friction_patch(0.9)
         rot = None
-    return _finish("cfg2", m, _fields(m, seed, "tanh", z0=z0, box=box), fks_placeholder(), mix, stick, rot, seed,
-                   meta=dict(rank=rank))
+    return _finish("cfg2", m, _fields(m, seed, "tanh", z0=z0, box=box), visc1 or fks_placeholder(), mix, stick, rot,
+                   seed, meta=dict(rank=rank))
 
 
 def cfg3(base=(128, 128, 128)) -> Case:
@@ -189,15 +190,15 @@ def cfg3(base=(128, 128, 128)) -> Case:
     return _finish("cfg3", m, _fields(m, seed, "tanh"), sheppard_wright_aa6061(), mix, stick, rot, seed)
 
 
-def cfg4(dims=(256, 256, 256)) -> Case:
+def cfg4(dims=(256, 256, 256), visc1=None) -> Case:
     """fluid region of the two-region case: hex 256^3, NortonHoff, qfric skipped (SURVEY D-1)."""
     seed = SEED0 + 4
     m = _hex(dims, 0.25e-3)
     top = m.patch_id("zmax")
     mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
     rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
-    return _finish("cfg4", m, _fields(m, seed, "tanh"), norton_hoff_placeholder(), mix, P.no_friction_patch(0.9), rot,
-                   seed)
+    return _finish("cfg4", m, _fields(m, seed, "tanh"), visc1 or norton_hoff_placeholder(), mix,
+                   P.no_friction_patch(0.9), rot, seed)
 
 
 def cfg5_slab(rank, n_ranks, dims_per_rank=(512, 512, 32)) -> Case:

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 import numpy as np
 
 from solidstateamfoam_b200 import cases
+from solidstateamfoam_b200 import params as P
 
 SHEAR = (1.0, 0.3, 0.1, 0.0, 1.0, 0.2, 0.0, 0.0, 1.0)
 GOLDEN_CASES = {
@@ -24,6 +25,17 @@ GOLDEN_CASES = {
     "cfg2_fks_cubic_celsius": lambda: cases.cfg2(dims=(5, 5, 4), units="Celsius"),
     "cfg3_poly_exponentialslip": lambda: cases.cfg3(base=(4, 4, 4)),
     "cfg4_nortonhoff": lambda: cases.cfg4(dims=(5, 5, 4)),
+    # other corners of the parameter space: FKS with b2, c2 != 1 (no pow shortcuts), a different cubic k(T);
+    # SheppardWright with other n, A and default limiters far away; NortonHoff with another exponent
+    "cfg2_fks_general_exponents": lambda: cases.cfg2(
+        dims=(6, 5, 4), k_coeffs=(35.0, -0.05, 3e-4, -2e-7),
+        visc1=P.fks(a1=2.1e8, a2=0.6e8, b1=0.05, b2=0.7, b3=1.3, e0=0.01, c1=3.0, c2=2.5, Tm=900.0, Ta=300.0, rho=2650.0,
+                    nuMin=1e-8, nuMax=1e6, eDotMin=1e-9)),
+    "cfg1_sheppardwright_other_alloy": lambda: cases.cfg1(
+        dims=(6, 5, 4), visc1=P.sheppard_wright(sigmaR=3.1e7, Q=1.9e5, R=8.314, A=5.0e10, n=5.2, rho=2800.0, nuMin=1e-9,
+                                              nuMax=1e7, eDotMin=1e-10)),
+    "cfg4_nortonhoff_other_exponent": lambda: cases.cfg4(
+        dims=(5, 4, 4), visc1=P.norton_hoff(mu0=3e7, m=0.35, rho=2700.0, nuMin=1e-7, nuMax=1e5, strainRateEffMin=1e-8)),
 }
 
 

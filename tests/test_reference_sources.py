@@ -30,6 +30,14 @@ CASES = {
     "cfg3_poly_exponentialslip": lambda: cases.cfg3(base=(6, 6, 6)),
     "cfg4_nortonhoff": lambda: cases.cfg4(dims=(6, 5, 5)),
 }
+# other corners of the parameter space (FKS with b2, c2 != 1, another cubic k(T), other alloys / exponents)
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from gen_reference_golden import GOLDEN_CASES  # noqa: E402
+
+for _k in ("cfg2_fks_general_exponents", "cfg1_sheppardwright_other_alloy", "cfg4_nortonhoff_other_exponent"):
+    CASES[_k] = GOLDEN_CASES[_k]
 
 
 @pytest.mark.parametrize("form", [O.FAITHFUL, O.FUSED], ids=["faithful", "fused"])
