@@ -501,3 +501,20 @@ def test_div_dev_rho_reff_explicit(ctx, name):
     gi, gb = ctx.download(P.F_DIVDEVRHOREFF)
     check_field("divDevRhoReff (explicit)", np.concatenate([gi, gb]), oc.field(P.F_DIVDEVRHOREFF), True)
     assert np.abs(gi).max() > 0
+
+
+def test_rerun_is_bitwise_deterministic(ctx):
+    """No FP64 atomics anywhere on the path: repeated updates on the same inputs give identical bits (this is also
+    the race detector of the tiled kernels: a missed barrier or a stale shared-memory tile would show up here)."""
+    case = cases.cfg3(base=(16, 16, 16))
+    ctx.load_case(case)
+    first = None
+    for rep in range(4):
+        ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
+        ctx.interface_correct(ctx.interface_delta_n())
+        snap = [np.concatenate(ctx.download(f)) for f in case.outputs + [P.F_GRADU, P.F_CURVATURE, P.F_GRADALPHA]]
+        if first is None:
+            first = snap
+        else:
+            for a, b in zip(first, snap):
+                assert np.array_equal(a, b, equal_nan=True), rep
