@@ -175,7 +175,8 @@ def cpu_arm(workload: str, steps: int, warmup: int, threads: int | None = None, 
         O.update_multi(ocs, cs[0].params, form=O.FAITHFUL)
     dt = time.perf_counter() - t0
     sample = (f"{steps} updates of a {nx}x{ny}x{lpt * threads} hex box ({cells} cells) split into {threads} z-slabs, "
-              f"one per host thread; oracle faithful field-at-a-time restatement (OpenFOAM unavailable offline), "
+              f"one per host thread; oracle faithful field-at-a-time restatement (OpenFOAM unavailable offline; its model "
+              f"expressions are bit-identical to the reference's own sources, tests/test_reference_sources.py), "
               f"{workload} models")
     return cells * steps / dt / 1e6, threads, sample, dt / steps * 1e3
 
