@@ -17,8 +17,19 @@ from solidstateamfoam_b200 import params as P
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libssam_ref.so")
+_SO_GPU = os.path.join(_HERE, "_ref", "libssam_ref_gpu.so")  # same harness, GPU-backed viscosity models (integration/openfoam)
 REFERENCE_TREE = os.environ.get("SSAM_REFERENCE_TREE", "/root/reference")
 _lib = None
+_lib_gpu = None
+
+
+def build_shim() -> bool:
+    """oracle/_ref/libssam_ref_gpu.so (Makefile target `shim`); needs libssam_gpu.so to be built already."""
+    if os.path.isdir(REFERENCE_TREE) and not os.environ.get("SSAM_REF_NOBUILD"):
+        r = subprocess.run(["make", "-C", _HERE, "shim", f"REF={REFERENCE_TREE}"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building the OpenFOAM-shim demo failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return os.path.exists(_SO_GPU)
 
 
 def build() -> bool:
@@ -37,29 +48,39 @@ def available() -> bool:
         return False
 
 
-def lib():
-    global _lib
+def lib(gpu: bool = False):
+    global _lib, _lib_gpu
+    if gpu:
+        if _lib_gpu is None:
+            if not build_shim():
+                raise RuntimeError("oracle/_ref/libssam_ref_gpu.so is absent and there is no reference tree to build it from")
+            _lib_gpu = _bind(C.CDLL(_SO_GPU))
+        return _lib_gpu
     if _lib is None:
         if not build():
             raise RuntimeError("oracle/_ref/libssam_ref.so is absent and there is no reference tree to build it from")
-        L = C.CDLL(_SO)
-        vp, dp = C.c_void_p, C.POINTER(C.c_double)
-        L.ref_create.restype = vp
-        L.ref_create.argtypes = [C.POINTER(P.MeshDesc), C.POINTER(C.c_char_p), C.c_char_p]
-        L.ref_destroy.argtypes = [vp]
-        L.ref_last_error.restype = C.c_char_p
-        L.ref_last_error.argtypes = [vp]
-        L.ref_info.restype = C.c_char_p
-        L.ref_info.argtypes = [vp]
-        L.ref_set_scalar.argtypes = [vp, C.c_char_p, dp, C.c_int]
-        L.ref_construct.argtypes = [vp, C.c_int]
-        L.ref_thermo_correct.argtypes = [vp]
-        L.ref_friction_correct.argtypes = [vp]
-        L.ref_eval.argtypes = [vp, C.c_char_p, dp]
-        L.ref_bc_rotational_slip.argtypes = [vp, C.c_char_p, dp]
-        L.ref_calculate_strain.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp, dp]
-        _lib = L
+        _lib = _bind(C.CDLL(_SO))
     return _lib
+
+
+def _bind(L):
+    vp, dp = C.c_void_p, C.POINTER(C.c_double)
+    L.ref_create.restype = vp
+    L.ref_create.argtypes = [C.POINTER(P.MeshDesc), C.POINTER(C.c_char_p), C.c_char_p]
+    L.ref_destroy.argtypes = [vp]
+    L.ref_last_error.restype = C.c_char_p
+    L.ref_last_error.argtypes = [vp]
+    L.ref_info.restype = C.c_char_p
+    L.ref_info.argtypes = [vp]
+    L.ref_set_scalar.argtypes = [vp, C.c_char_p, dp, C.c_int]
+    L.ref_construct.argtypes = [vp, C.c_int]
+    L.ref_thermo_correct.argtypes = [vp]
+    L.ref_friction_correct.argtypes = [vp]
+    L.ref_eval.argtypes = [vp, C.c_char_p, dp]
+    L.ref_bc_rotational_slip.argtypes = [vp, C.c_char_p, dp]
+    L.ref_calculate_strain.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp, dp]
+    L.ref_set_U.argtypes = [vp, dp, C.POINTER(C.c_int32)]
+    return L
 
 
 class ReferenceError_(RuntimeError):
@@ -69,16 +90,17 @@ class ReferenceError_(RuntimeError):
 class ReferenceCase:
     """The reference's mixture + friction model on one mesh, reading `<case_dir>/constant/{transport,friction}Properties`."""
 
-    def __init__(self, mesh, case_dir: str):
+    def __init__(self, mesh, case_dir: str, gpu: bool = False):
         self.mesh = mesh
+        self.L = lib(gpu)
         self._desc, self._keep = P.mesh_desc(mesh)
         names = (C.c_char_p * mesh.nPatches)(*[n.encode() for n in mesh.patchName])
-        self.h = C.c_void_p(lib().ref_create(C.byref(self._desc), names, case_dir.encode()))
+        self.h = C.c_void_p(self.L.ref_create(C.byref(self._desc), names, case_dir.encode()))
         self.nTot = mesh.nCells + mesh.nBoundaryFaces
 
     def close(self):
         if self.h:
-            lib().ref_destroy(self.h)
+            self.L.ref_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -89,33 +111,33 @@ class ReferenceCase:
 
     def _chk(self, st):
         if st != 0:
-            raise ReferenceError_(lib().ref_last_error(self.h).decode())
+            raise ReferenceError_(self.L.ref_last_error(self.h).decode())
 
     def set(self, name: str, values, as_file: bool = False):
         v = np.ascontiguousarray(values, dtype=np.float64)
         assert v.shape == (self.nTot,), (name, v.shape)
-        self._chk(lib().ref_set_scalar(self.h, name.encode(), v.ctypes.data_as(C.POINTER(C.c_double)), 1 if as_file else 0))
+        self._chk(self.L.ref_set_scalar(self.h, name.encode(), v.ctypes.data_as(C.POINTER(C.c_double)), 1 if as_file else 0))
 
     def construct(self, with_friction: bool = True):
-        self._chk(lib().ref_construct(self.h, 1 if with_friction else 0))
+        self._chk(self.L.ref_construct(self.h, 1 if with_friction else 0))
 
     def thermo_correct(self):
-        self._chk(lib().ref_thermo_correct(self.h))
+        self._chk(self.L.ref_thermo_correct(self.h))
 
     def friction_correct(self):
-        self._chk(lib().ref_friction_correct(self.h))
+        self._chk(self.L.ref_friction_correct(self.h))
 
     def eval(self, what: str) -> np.ndarray:
         n = self.mesh.nFaces if what in ("muf", "nuf") else self.nTot
         out = np.zeros(n)
-        self._chk(lib().ref_eval(self.h, what.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
+        self._chk(self.L.ref_eval(self.h, what.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
     def bc_rotational_slip(self, patch_name: str) -> np.ndarray:
         """updateCoeffs() of the *RotationalSlip patch field described in <case_dir>/0/U -> U_b [n, 3]"""
         p = self.mesh.patch_id(patch_name)
         out = np.zeros((int(self.mesh.patchSize[p]), 3))
-        self._chk(lib().ref_bc_rotational_slip(self.h, patch_name.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
+        self._chk(self.L.ref_bc_rotational_slip(self.h, patch_name.encode(), out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
     def calculate_strain(self, deltaT: float, gradU, p_rgh, epsilonEq):
@@ -126,10 +148,20 @@ class ReferenceCase:
         pr = np.ascontiguousarray(p_rgh, dtype=np.float64)
         eq = np.array(epsilonEq, dtype=np.float64)
         Z, sf, vm = np.zeros(self.nTot), np.zeros(self.nTot), np.zeros(self.nTot)
-        self._chk(lib().ref_calculate_strain(self.h, deltaT, g.ctypes.data_as(dp), pr.ctypes.data_as(dp),
+        self._chk(self.L.ref_calculate_strain(self.h, deltaT, g.ctypes.data_as(dp), pr.ctypes.data_as(dp),
                                              eq.ctypes.data_as(dp), Z.ctypes.data_as(dp), sf.ctypes.data_as(dp),
                                              vm.ctypes.data_as(dp)))
         return {"Z": Z, "sigmaf": sf, "epsilonEq": eq, "sigmavm": vm}
 
+    def set_U(self, U, patch_kinds=None):
+        """U incl. boundary values [nTot, 3] and the snGrad kind of each patch (GPU-backed models only)"""
+        u = np.ascontiguousarray(U, dtype=np.float64).reshape(-1)
+        assert u.size == 3 * self.nTot
+        k = None
+        if patch_kinds is not None:
+            self._kinds = np.ascontiguousarray(patch_kinds, dtype=np.int32)
+            k = self._kinds.ctypes.data_as(C.POINTER(C.c_int32))
+        self._chk(self.L.ref_set_U(self.h, u.ctypes.data_as(C.POINTER(C.c_double)), k))
+
     def info(self) -> str:
-        return lib().ref_info(self.h).decode()
+        return self.L.ref_info(self.h).decode()

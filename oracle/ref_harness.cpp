@@ -133,16 +133,53 @@ ref_case* ref_create(const ssam_mesh_desc* m, const char* const* patchNames, con
         mesh.CfPtr->values()[size_t(mesh.nInternalFaces + b)] = cf;
         mesh.magSfPtr->values()[size_t(mesh.nInternalFaces + b)] = m->magSf_b[b];
     }
+    {
+        fvMesh::GeometryStash& g = mesh.stash;
+        const int nF = m->nFaces, nIF = m->nInternalFaces, nC = m->nCells, nB = nF - nIF, nP = m->nPatches;
+        g.owner.assign(m->owner, m->owner + nF);
+        g.neighbour.assign(m->neighbour, m->neighbour + nIF);
+        g.patchStart.assign(m->patchStart, m->patchStart + nP);
+        g.patchSize.assign(m->patchSize, m->patchSize + nP);
+        g.patchKind.assign(m->patchKind, m->patchKind + nP);
+        g.patchNbrRank.assign(m->patchNbrRank, m->patchNbrRank + nP);
+        g.patchUbc.assign(size_t(nP), SSAM_BC_VALUE);
+        g.Sf.assign(m->Sf, m->Sf + 3 * size_t(nF));
+        g.weights.assign(m->weights, m->weights + nF);
+        g.V.assign(m->V, m->V + nC);
+        g.C.assign(m->C, m->C + 3 * size_t(nC));
+        g.Cf_b.assign(m->Cf_b, m->Cf_b + 3 * size_t(nB));
+        g.magSf_b.assign(m->magSf_b, m->magSf_b + nB);
+        g.deltaCoeffs_b.assign(m->deltaCoeffs_b, m->deltaCoeffs_b + nB);
+    }
     c->U.reset(new volVectorField(mesh, "U"));
     c->Ut.reset(new volVectorField(mesh, "Ut"));
     c->phi.reset(new surfaceScalarField(mesh, "phi"));
     return reinterpret_cast<ref_case*>(c);
 }
 
+// U (internal then boundary values, AoS) and the snGrad kind of each patch of U: only the GPU-backed models of
+// integration/openfoam need them (the CPU models get mag(symm(grad U)) from the oracle through "__magSymmGradU")
+int ref_set_U(ref_case* h, const double* values, const int32_t* patchKinds) {
+    RefCase* c = RC(h);
+    return guarded(c, [&]() {
+        for (int i = 0; i < c->nTot; ++i) c->U->values()[size_t(i)] = vector(values[3 * i], values[3 * i + 1], values[3 * i + 2]);
+        if (patchKinds) c->mesh.stash.patchUbc.assign(patchKinds, patchKinds + c->mesh.bMesh.size());
+    });
+}
+
+#ifdef SSAM_WITH_GPU_SHIM
+}  // extern "C"
+#include "ssamGpuMesh.H"
+extern "C" {
+#endif
+
 void ref_destroy(ref_case* h) {
     RefCase* c = RC(h);
     c->friction.reset();
     c->thermo.reset();
+#ifdef SSAM_WITH_GPU_SHIM
+    ssamGpuMesh::release(c->mesh);
+#endif
     delete c;
 }
 const char* ref_last_error(ref_case* h) { return RC(h)->err.c_str(); }

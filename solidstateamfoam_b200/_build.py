@@ -109,6 +109,9 @@ def build_oracle_ref(verbose: bool = False) -> str | None:
     so = os.path.join(odir, "_ref", "libssam_ref.so")
     if os.path.isdir(ref):
         _run(["make", "-C", odir, "ref", f"REF={ref}"], verbose)
+        if os.path.exists(os.path.join(LIB, "libssam_gpu.so")):
+            # the drop-in demonstration: reference mixture / friction sources + integration/openfoam GPU models
+            _run(["make", "-C", odir, "shim", f"REF={ref}"], verbose)
     return so if os.path.exists(so) else None
 
 

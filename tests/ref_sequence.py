@@ -18,8 +18,10 @@ VOL_OUTPUTS = {"nu1": P.F_NU1, "nu2": P.F_NU2, "sigmaf": P.F_SIGMAF, "sigmay": P
                "rho": P.F_RHO, "cp": P.F_CP, "k": P.F_K, "qvisc": P.F_QVISC, "qfric": P.F_QFRIC}
 
 
-def run_reference(case, tmpdir=None):
-    """-> (dict name -> array, Info text).  The call order of createFluidFields.H + one time step."""
+def run_reference(case, tmpdir=None, gpu_shim=False):
+    """-> (dict name -> array, Info text).  The call order of createFluidFields.H + one time step.
+    gpu_shim: the same reference mixture / friction sources, but with the GPU-backed viscosity models of
+    integration/openfoam selected by the reference's own viscosityModel::New (oracle/Makefile target `shim`)."""
     d = tmpdir or tempfile.mkdtemp(prefix="ssam_ref_")
     cases.write_case_dir(d, case, eps0=1.0, mu0=1.0)
     m = case.mesh
@@ -32,9 +34,12 @@ def run_reference(case, tmpdir=None):
         oc.bc_rotational_slip(case.rotslip)
     oc.strain_rate(1.0, P.F_STRAINRATE)
     mag_symm = oc.field(P.F_STRAINRATE).copy()
+    U_all = oc.field(P.F_U).copy()
     oc.close()
 
-    rc = R.ReferenceCase(m, d)
+    rc = R.ReferenceCase(m, d, gpu=gpu_shim)
+    if gpu_shim:
+        rc.set_U(U_all, case.patch_u_bc)  # NortonHoff takes its strain rate from U on the device
     cat = np.concatenate
     rc.set("temp", cat([case.T_i, case.T_b]))
     rc.set("epsilonDotEq", np.full(n, 1.0))            # createFluidFields.H initial value (here: 1)

@@ -1,0 +1,50 @@
+"""The drop-in boundary, exercised with the reference's own code in the loop (GPU).
+
+oracle/_ref/libssam_ref_gpu.so (oracle/Makefile target `shim`) is the reference's mixture, friction-model, stick-model
+and boundary-condition sources, UNMODIFIED, compiled against the stand-in OpenFOAM headers, together with
+integration/openfoam/gpuViscosityModels.C -- GPU-backed SheppardWright / FKS / NortonHoff classes with the reference's
+names, TypeNames, constructor signature and dictionary keys, built INSTEAD of viscoPlasticModels/*.C.  The reference's
+own `viscosityModel::New` selects them from an unchanged transportProperties, the reference's own
+`incompressibleTwoPhaseThermalMixture::calcNu()` calls their `correct()`, and the reference's stick models look up
+the `sigmay` they register.  Every field is compared with the outputs frozen from the all-CPU reference sources
+(tests/golden/reference_sources.npz): <= 1e-11 relative.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import pyref as R
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from gen_reference_golden import GOLDEN_CASES, inputs_digest  # noqa: E402
+
+from helpers import check_field  # noqa: E402
+from ref_sequence import run_reference  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sources.npz"))
+
+
+def _shim_available():
+    try:
+        return R.build_shim()
+    except RuntimeError:
+        return False
+
+
+@pytest.mark.skipif(not _shim_available(), reason="no reference tree and no prebuilt oracle/_ref/libssam_ref_gpu.so")
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_reference_code_with_gpu_backed_viscosity_models(name, tmp_path):
+    case = GOLDEN_CASES[name]()
+    assert inputs_digest(case) == bytes(GOLDEN[name + "/inputs_sha256"]).decode()
+    got, info = run_reference(case, str(tmp_path), gpu_shim=True)
+    assert "Selecting incompressible transport model" in info  # the reference's run-time selection picked them
+    keys = [k.split("/", 1)[1] for k in GOLDEN.files
+            if k.startswith(name + "/") and not k.endswith("inputs_sha256") and not k.endswith("bc_Ub")]
+    assert sorted(keys) == sorted(got)
+    for k in keys:
+        # nu2 (OpenFOAM's Newtonian, CPU on both sides), rho, cp are pure CPU reference code: identical
+        check_field(f"{name}/{k}", got[k], GOLDEN[name + "/" + k], k in ("nu2", "rho", "cp"))
