@@ -2,11 +2,13 @@
 
 oracle/_ref/libssam_ref_gpu.so (oracle/Makefile target `shim`) is the reference's mixture, friction-model, stick-model
 and boundary-condition sources, UNMODIFIED, compiled against the stand-in OpenFOAM headers, together with
-integration/openfoam/gpuViscosityModels.C -- GPU-backed SheppardWright / FKS / NortonHoff classes with the reference's
-names, TypeNames, constructor signature and dictionary keys, built INSTEAD of viscoPlasticModels/*.C.  The reference's
-own `viscosityModel::New` selects them from an unchanged transportProperties, the reference's own
-`incompressibleTwoPhaseThermalMixture::calcNu()` calls their `correct()`, and the reference's stick models look up
-the `sigmay` they register.  Every field is compared with the outputs frozen from the all-CPU reference sources
+integration/openfoam/gpuViscosityModels.C and gpuStickModels.C -- GPU-backed SheppardWright / FKS / NortonHoff and
+constantSlipStick / exponentialSlipStick classes with the reference's names, TypeNames, constructor signatures and
+dictionary keys, built INSTEAD of viscoPlasticModels/*.C and stickModels/{constant,exponential}SlipStick/*.C.  The
+reference's own `viscosityModel::New` / `stickModel::New` select them from unchanged transportProperties /
+frictionProperties, the reference's own `incompressibleTwoPhaseThermalMixture::calcNu()` and
+`incompressibleFrictionModel::correct()` call them, and the GPU stick models look up the `sigmay` the GPU viscosity
+model registered.  Every field is compared with the outputs frozen from the all-CPU reference sources
 (tests/golden/reference_sources.npz): <= 1e-11 relative.
 """
 import os
@@ -37,11 +39,13 @@ def _shim_available():
 
 @pytest.mark.skipif(not _shim_available(), reason="no reference tree and no prebuilt oracle/_ref/libssam_ref_gpu.so")
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
-def test_reference_code_with_gpu_backed_viscosity_models(name, tmp_path):
+def test_reference_code_with_gpu_backed_models(name, tmp_path):
     case = GOLDEN_CASES[name]()
     assert inputs_digest(case) == bytes(GOLDEN[name + "/inputs_sha256"]).decode()
     got, info = run_reference(case, str(tmp_path), gpu_shim=True)
     assert "Selecting incompressible transport model" in info  # the reference's run-time selection picked them
+    if "qfric" in got:
+        assert "Selecting stick model" in info and "Center for patch zmax found to be at" in info
     keys = [k.split("/", 1)[1] for k in GOLDEN.files
             if k.startswith(name + "/") and not k.endswith("inputs_sha256") and not k.endswith("bc_Ub")]
     assert sorted(keys) == sorted(got)
