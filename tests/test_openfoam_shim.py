@@ -25,8 +25,6 @@ from gen_reference_golden import GOLDEN_CASES, inputs_digest  # noqa: E402
 from helpers import check_field  # noqa: E402
 from ref_sequence import run_reference  # noqa: E402
 
-pytestmark = pytest.mark.gpu
-
 GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sources.npz"))
 
 
@@ -37,6 +35,30 @@ def _shim_available():
         return False
 
 
+@pytest.mark.skipif(not _shim_available(), reason="no reference tree and no prebuilt oracle/_ref/libssam_ref_gpu.so")
+def test_shim_fails_loudly_without_a_gpu(tmp_path):
+    """No CPU fallback anywhere: without a CUDA device the GPU-backed model's constructor raises the library's error
+    as a FatalError through the reference's own viscosityModel::New / mixture constructor."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from solidstateamfoam_b200 import cases
+
+    case = GOLDEN_CASES["cfg2_fks_cubic_kelvin"]()
+    d = str(tmp_path)
+    cases.write_case_dir(d, case)
+    n = case.mesh.nCells + case.mesh.nBoundaryFaces
+    rc = R.ReferenceCase(case.mesh, d, gpu=True)
+    rc.set("temp", np.full(n, 500.0))
+    rc.set("epsilonDotEq", np.ones(n))
+    rc.set("alpha.metal", np.ones(n), as_file=True)
+    with pytest.raises(R.ReferenceError_) as e:
+        rc.construct(with_friction=False)
+    assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.gpu
 @pytest.mark.skipif(not _shim_available(), reason="no reference tree and no prebuilt oracle/_ref/libssam_ref_gpu.so")
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
 def test_reference_code_with_gpu_backed_models(name, tmp_path):
