@@ -260,6 +260,8 @@ int ref_bc_rotational_slip(ref_case* h, const char* patchName, double* out) {
         if (pi < 0) throw FoamFatal(std::string("no patch ") + patchName);
         const polyPatch& pp = c->mesh.boundaryMesh()[pi];
         fvPatch patch;
+        patch.mesh_ = &c->mesh;
+        patch.index_ = pi;
         for (label i = 0; i < pp.n; ++i) patch.Cf_.push_back(c->mesh.Cf().values()[size_t(c->mesh.nInternalFaces + pp.start + i)]);
         DimensionedField<vector, volMesh> iF;
         const word type(pd.lookup("type"));

@@ -74,3 +74,21 @@ def test_reference_code_with_gpu_backed_models(name, tmp_path):
     for k in keys:
         # nu2 (OpenFOAM's Newtonian, CPU on both sides), rho, cp are pure CPU reference code: identical
         check_field(f"{name}/{k}", got[k], GOLDEN[name + "/" + k], k in ("nu2", "rho", "cp"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not _shim_available(), reason="no reference tree and no prebuilt oracle/_ref/libssam_ref_gpu.so")
+@pytest.mark.parametrize("name", [k for k in GOLDEN_CASES if k + "/bc_Ub" in GOLDEN.files])
+def test_gpu_backed_rotational_slip_patch_fields(name, tmp_path):
+    """integration/openfoam's *RotationalSlipFvPatchVectorField (built instead of boundaryConditions/*.C): constructed
+    from the patch's dictionary in 0/U, updateCoeffs() on the device, values mirrored into the patch field"""
+    from solidstateamfoam_b200 import cases
+    from solidstateamfoam_b200 import params as P
+
+    case = GOLDEN_CASES[name]()
+    d = str(tmp_path)
+    cases.write_case_dir(d, case)
+    rc = R.ReferenceCase(case.mesh, d, gpu=True)
+    ub = rc.bc_rotational_slip("zmax").reshape(-1)
+    check_field(f"{name}/U_b", ub, GOLDEN[name + "/bc_Ub"], case.rotslip.model == P.ROTSLIP_CONSTANT)
+    assert np.abs(ub).max() > 0
