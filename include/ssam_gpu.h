@@ -198,8 +198,10 @@ SSAM_API ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking);
 SSAM_API int ssam_abi_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 SSAM_API int64_t ssam_launch_count(const ssam_ctx* ctx);
-/* Fused cell-kernel variant: 1 (default) = tiled, inputs of 256 consecutive cells staged in shared memory
- * by 1-D bulk async copies; 0 = one thread per cell with direct global loads.  Results are identical. */
+/* Fused cell-kernel variant: 2 (default) = persistent self-pipelined tiles (the bulk copies of a CTA's next tile
+ * land while it runs the FP64 chain of the current one); 1 = tiled, one CTA per tile: inputs of 256 consecutive
+ * cells staged in shared memory by 1-D bulk async copies; 0 = one thread per cell with direct global loads.
+ * Results are bit-identical. */
 SSAM_API ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant);
 /* Cell layout of the device planes, to be chosen before ssam_mesh_set:
  *   SSAM_LAYOUT_CALLER  (0) the caller's cell numbering;

@@ -105,6 +105,13 @@ def fks_placeholder():
                  rho=2700.0, nuMin=1e-6, nuMax=1e4, eDotMin=1e-6)
 
 
+def fks_general_exponents():
+    """FKS with b2, c2 != 1: no pow(x, 1) shortcut applies (two extra pow per cell); same values as the golden case
+    cfg2_fks_general_exponents (tests/golden/gen_reference_golden.py)"""
+    return P.fks(a1=2.1e8, a2=0.6e8, b1=0.05, b2=0.7, b3=1.3, e0=0.01, c1=3.0, c2=2.5, Tm=900.0, Ta=300.0, rho=2650.0,
+                 nuMin=1e-8, nuMax=1e6, eDotMin=1e-9)
+
+
 def norton_hoff_placeholder():
     return P.norton_hoff(mu0=1e8, m=0.2, rho=2700.0, nuMin=1e-6, nuMax=1e4, strainRateEffMin=1e-6)
 

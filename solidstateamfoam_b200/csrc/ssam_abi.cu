@@ -49,7 +49,10 @@ struct ssam_ctx {
     int bandwidthTiles = 0;  // ceil(max(neighbour - owner) / TILE)
     int hostChunks = -1;  // >= 0 overrides the chunk count of the host-staged pipeline (0/1 = unpipelined)
     int nTilesOversize = 0;
-    int cellKernel = 1;  // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged
+    // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged, one CTA per tile; 2 = persistent
+    // self-pipelined tiles (default)
+    int cellKernel = 2;
+    int pipeGridCap = 0;  // > 0: cap on the persistent kernel's grid (experiments)
     // cell layout: 0 = the caller's numbering, 1 = tile-compact when it pays (default), 2 = always tile-compact
     int layoutMode = 1;
     int* perm = nullptr;      // device position i holds the caller's cell perm[i] (nullptr = identity)
@@ -788,8 +791,63 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
     CU(cudaGetLastError());
     return SSAM_OK;
 }
+// persistent, self-pipelined variant: one CTA per resident slot, looping over the work list
+template <int M>
+ssam_status launchPipeOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, int count, cudaStream_t stream) {
+    if (count == 0) return SSAM_OK;
+    UpdateArgs a = a0;
+    a.tileList = list;
+    a.tileCount = count;
+    if (list) {
+        if (list == ctx->tileListInterior) {
+            a.tileDesc = ctx->descInterior;
+        } else if (list == ctx->tileListCoupled) {
+            a.tileDesc = ctx->descCoupled;
+        } else if (list == ctx->tileOrder) {
+            a.tileDesc = ctx->descOrder;
+        } else {
+            a.tileDesc = ctx->tileDesc + (list - ctx->tileIota);  // a range of the identity list
+        }
+    }
+    static int residentCtas[64] = {0};  // per device: SMs x CTAs per SM of this instantiation
+    const int smem = int(sizeof(TileSmem));
+    int& slots = residentCtas[ctx->device & 63];
+    if (slots == 0) {
+        CU(cudaFuncSetAttribute(k_cells_pipe<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int perSm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_cells_pipe<M>, TILE, size_t(smem)));
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        CHECK(perSm > 0 && sms > 0, SSAM_ERR_CUDA, "k_cells_pipe does not fit on this device");
+        slots = perSm * sms;
+    }
+    int grid = std::min(count, slots);
+    if (ctx->pipeGridCap > 0) grid = std::min(grid, ctx->pipeGridCap);
+    // the L2 prefetch distances are given in tiles ahead of the CTA's NEXT tile
+    if (a.pfDist > 0) {
+        a.pfDist += grid;
+        a.pfDistU += grid;
+    }
+    k_cells_pipe<M><<<grid, TILE, smem, stream>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return SSAM_OK;
+}
+ssam_status launchCellsPipe(ssam_ctx* ctx, const UpdateArgs& a, int model1, const int* list, int count,
+                            cudaStream_t stream) {
+    switch (model1) {
+        case SSAM_VISC_NEWTONIAN: return launchPipeOne<SSAM_VISC_NEWTONIAN>(ctx, a, list, count, stream);
+        case SSAM_VISC_SHEPPARD_WRIGHT: return launchPipeOne<SSAM_VISC_SHEPPARD_WRIGHT>(ctx, a, list, count, stream);
+        case SSAM_VISC_FKS: return launchPipeOne<SSAM_VISC_FKS>(ctx, a, list, count, stream);
+        case SSAM_VISC_NORTON_HOFF: return launchPipeOne<SSAM_VISC_NORTON_HOFF>(ctx, a, list, count, stream);
+        case TILED_GRAD: return launchPipeOne<TILED_GRAD>(ctx, a, list, count, stream);
+        case TILED_STRAIN: return launchPipeOne<TILED_STRAIN>(ctx, a, list, count, stream);
+    }
+    return fail(ctx, SSAM_ERR_UNKNOWN_MODEL, "Unknown viscosityModel type");
+}
+
 ssam_status launchCellsTiled(ssam_ctx* ctx, const UpdateArgs& a, int model1, const int* list, int count,
                              cudaStream_t stream) {
+    if (ctx->cellKernel == 2) return launchCellsPipe(ctx, a, model1, list, count, stream);
 #define SSAM_TILED(M)                                                                   \
     case M:                                                                             \
         return list ? launchTiledOne<M, true>(ctx, a, list, count, stream)              \
@@ -813,7 +871,7 @@ ssam_status gradOrStrain(ssam_ctx* ctx, bool strain, double factor, int outField
     fillMeshArgs(ctx, a);
     a.pfDist = ctx->pfDist;
     a.pfDistU = a.pfDist + ctx->bandwidthTiles;
-    const bool tiled = ctx->cellKernel == 1;
+    const bool tiled = ctx->cellKernel >= 1;
     if (strain) {
         TRY(ensureField(ctx, outField));
         a.strainOut = ctx->plane[outField][0];
@@ -935,9 +993,16 @@ struct PermutedMesh {
     std::vector<double> Sf, w, V, C;
 };
 
+// SSAM_TILE_ORDER=0: tiles in seed (caller) order; 1 (default): Morton order of the tile centroids within 16 coarse
+// caller-order buckets
+int tileOrderModeFromEnv() {
+    const char* e = std::getenv("SSAM_TILE_ORDER");
+    return e ? std::atoi(e) : 1;
+}
+
 // -> perm (library position -> caller cell); returns false when clustering does not pay
-bool computeCompactOrder(int layoutMode, const ssam_mesh_desc* m, std::vector<int>& perm, double& remotePerCellCaller,
-                         double& remotePerCellCompact) {
+bool computeCompactOrder(int layoutMode, int tileOrderMode, const ssam_mesh_desc* m, std::vector<int>& perm,
+                         double& remotePerCellCaller, double& remotePerCellCompact) {
     const int nC = m->nCells, nIF = m->nInternalFaces;
     const int nB = (nC + RUN - 1) / RUN;
     std::vector<std::vector<int>> nb(nB);
@@ -1007,6 +1072,58 @@ bool computeCompactOrder(int layoutMode, const ssam_mesh_desc* m, std::vector<in
         for (int k = 0; k < nMem; ++k) (whole ? full : partial).push_back(members[k]);
     }
     std::sort(partial.begin(), partial.end());
+    // Order of the complete tiles in memory = order in which the persistent kernel walks them.  In seed order the
+    // bricks of a blockMesh box follow x, y, z, so a tile's z-neighbours are one whole layer of bricks away
+    // (512x512 planes: 140 MB of traffic, more than the 126 MB L2 keeps -> the out-of-tile gathers miss).  A Morton
+    // (Z-order) curve over the tile centroids bounds the reuse distance by the surface of a sub-cube instead.
+    // Integer/geometry preprocessing only: per-cell face order, and with it every result bit, is unchanged.
+    if (tileOrderMode == 1 && full.size() >= size_t(8 * RUNS_PER_TILE)) {
+        const size_t nT = full.size() / RUNS_PER_TILE;
+        std::vector<double> cen(nT * 3, 0.0);
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (size_t t = 0; t < nT; ++t) {
+            for (int r = 0; r < RUNS_PER_TILE; ++r) {
+                const int b = full[t * RUNS_PER_TILE + size_t(r)];
+                // centroid of a run ~ mean of its first and last cell centre (runs are mesh lines)
+                const int c0 = b * RUN, c1 = std::min(nC, (b + 1) * RUN) - 1;
+                for (int k = 0; k < 3; ++k)
+                    cen[t * 3 + size_t(k)] += 0.5 * (m->C[size_t(c0) * 3 + size_t(k)] + m->C[size_t(c1) * 3 + size_t(k)]);
+            }
+            for (int k = 0; k < 3; ++k) {
+                cen[t * 3 + size_t(k)] /= RUNS_PER_TILE;
+                lo[k] = std::min(lo[k], cen[t * 3 + size_t(k)]);
+                hi[k] = std::max(hi[k], cen[t * 3 + size_t(k)]);
+            }
+        }
+        const double ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-300});
+        auto spread = [](unsigned long long v) {  // 21 bits -> every third bit
+            v &= 0x1fffffull;
+            v = (v | v << 32) & 0x1f00000000ffffull;
+            v = (v | v << 16) & 0x1f0000ff0000ffull;
+            v = (v | v << 8) & 0x100f00f00f00f00full;
+            v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+            v = (v | v << 2) & 0x1249249249249249ull;
+            return v;
+        };
+        std::vector<std::pair<unsigned long long, int>> key(nT);
+        for (size_t t = 0; t < nT; ++t) {
+            unsigned long long q[3];
+            for (int k = 0; k < 3; ++k)  // the same physical length per level on every axis
+                q[k] = (unsigned long long)(std::min(1.0, (cen[t * 3 + size_t(k)] - lo[k]) / ext) * 524287.0);  // 19 bits
+            key[t] = {spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), int(t)};
+            // coarse key: position of the tile's first run in the CALLER's order, in 16 buckets -- keeps the layout
+            // monotone enough for the chunk pipeline of the host-staged entry point (a caller chunk maps to a
+            // bounded range of tiles and vice versa)
+            const unsigned long long bucket = nT >= 1024 ? (unsigned long long)full[t * RUNS_PER_TILE] * 16ull / (unsigned long long)nB : 0ull;
+            key[t].first |= bucket << 58;  // the Morton key uses bits 0..56
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<int> ordered;
+        ordered.reserve(full.size());
+        for (const auto& kt : key)
+            for (int r = 0; r < RUNS_PER_TILE; ++r) ordered.push_back(full[size_t(kt.second) * RUNS_PER_TILE + size_t(r)]);
+        full.swap(ordered);
+    }
     perm.clear();
     perm.reserve(size_t(nC));
     for (const std::vector<int>* lst : {&full, &partial})
@@ -1145,7 +1262,8 @@ ssam_status ssam_set_host_chunks(ssam_ctx* ctx, int n) {
 
 ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant) {
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
-    CHECK(variant == 0 || variant == 1, SSAM_ERR_INVALID, "cell kernel variant must be 0 (direct) or 1 (tiled)");
+    CHECK(variant >= 0 && variant <= 2, SSAM_ERR_INVALID,
+          "cell kernel variant must be 0 (direct), 1 (tiled, one CTA per tile) or 2 (persistent, self-pipelined)");
     ctx->cellKernel = variant;
     return SSAM_OK;
 }
@@ -1168,7 +1286,7 @@ ssam_status ssam_compact_cell_order(const ssam_mesh_desc* m, int32_t* order, dou
             return fail(nullptr, SSAM_ERR_INVALID, "owner / neighbour label out of range");
     std::vector<int> perm;
     double a = 0, b = 0;
-    const bool use = computeCompactOrder(SSAM_LAYOUT_AUTO, m, perm, a, b);
+    const bool use = computeCompactOrder(SSAM_LAYOUT_AUTO, tileOrderModeFromEnv(), m, perm, a, b);
     for (int i = 0; i < m->nCells; ++i) order[i] = perm[size_t(i)];
     if (remote_caller) *remote_caller = a;
     if (remote_compact) *remote_compact = b;
@@ -1223,7 +1341,8 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
             CHECK(m->owner[f] >= 0 && m->owner[f] < m->nCells &&
                       (f >= m->nInternalFaces || (m->neighbour[f] >= 0 && m->neighbour[f] < m->nCells)),
                   SSAM_ERR_INVALID, "owner / neighbour label out of range");
-        if (computeCompactOrder(ctx->layoutMode, m, pm.perm, ctx->remotePerCellCaller, ctx->remotePerCellCompact)) {
+        if (computeCompactOrder(ctx->layoutMode, tileOrderModeFromEnv(), m, pm.perm, ctx->remotePerCellCaller,
+                                ctx->remotePerCellCompact)) {
             permuteMesh(m, pm);
             mm = *m;
             mm.owner = pm.owner.data();
@@ -2025,7 +2144,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     //   comm stream: pack + NCCL(U,temp,alpha1) -> coupled tiles -> pack + NCCL(epsilonDotEq[,...]) -+-> boundary faces
     // so both halo exchanges and the tiles that need them hide behind the interior tiles.
     const bool haloInputs = ctx->nProcPatches && (flags & 2);
-    const bool split = ctx->nProcPatches > 0 && ctx->cellKernel == 1;
+    const bool split = ctx->nProcPatches > 0 && ctx->cellKernel >= 1;
     if (ctx->nProcPatches && !ctx->commStream) {
         // highest priority: the comm stream's small kernels must get SM slots as soon as CTAs of the
         // interior-tile kernel retire, not after its whole grid has been dispatched
@@ -2077,7 +2196,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
                 TRY(launchCellsTiled(ctx, a, model1, ctx->tileIota + t0, t1 - t0, ctx->stream));
                 CU(cudaEventRecord(plan->evOut[k], ctx->stream));
             }
-        } else if (ctx->cellKernel == 1) {
+        } else if (ctx->cellKernel >= 1) {
             TRY(launchCellsTiled(ctx, a, model1, ctx->tileOrder, ctx->nTiles, ctx->stream));
         } else {
             TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
@@ -2323,7 +2442,7 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
     // itself and its two neighbours)
     int nChunks = ctx->hostChunks >= 0 ? std::min(ctx->hostChunks, 64) : std::min(16, ctx->nTiles / 1024);
     while (nChunks > 1 && (ctx->nTiles + nChunks - 1) / nChunks < ctx->bandwidthTiles + 1) --nChunks;
-    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel == 1 && ctx->nTilesOversize == 0)
+    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel >= 1 && ctx->nTilesOversize == 0)
         return updateFusedHostPipelined(ctx, p, io, nChunks);
     return updateFusedHostSimple(ctx, p, io);
 }

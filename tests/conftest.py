@@ -12,6 +12,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_count() -> int:
+    """number of CUDA devices through the driver API (no torch import, no context created)"""
+    import ctypes
+
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+    except OSError:
+        return 0
+    n = ctypes.c_int(0)
+    if cu.cuInit(0) != 0 or cu.cuDeviceGetCount(ctypes.byref(n)) != 0:
+        return 0
+    return n.value
+
+
+def pytest_collection_modifyitems(config, items):
+    """gpu-marked tests are skipped (not failed) on a box without a CUDA device"""
+    if _cuda_device_count() > 0:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this box")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _native_build():
     """Build the native pieces once (no-ops when the in-tree .so files are current)."""

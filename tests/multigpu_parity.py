@@ -94,7 +94,7 @@ def main():
     for which in (P.ADDR_HALO_SEND_CELLS, P.ADDR_HALO_PATCH_OFFSETS, P.ADDR_EXTRA_FACE, P.ADDR_EXTRA_OTHER):
         assert ctx.addressing(which).tobytes() == oc.addressing(which).tobytes(), P.ADDR_NAMES[which]
     worst = 0.0
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.set_cell_kernel(variant)
         ctx.update_fused(case.params, capi.FUSED_HALO_INPUTS | capi.FUSED_WRITE_GRAD)
         for f in case.outputs + [P.F_GRADU, P.F_U, P.F_T, P.F_ALPHA1]:

@@ -85,9 +85,9 @@ def test_cfg3_polyhedral_mid_size(ctx):
     """~700k-cell polyhedral mesh (two refinement levels): both cell-kernel variants against the oracle"""
     case = cases.cfg3(base=(64, 64, 64))
     ctx.load_case(case)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.set_cell_kernel(variant)
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
         oc = oracle_update(case, O.FUSED, ctx=ctx)
         compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU])
-    ctx.set_cell_kernel(1)
+    ctx.set_cell_kernel(2)

@@ -51,7 +51,7 @@ def test_integer_addressing_bit_exact(ctx, name):
         assert got.tobytes() == ref.tobytes(), f"{P.ADDR_NAMES[which]} differs"
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["direct", "tiled"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["direct", "tiled", "pipe"])
 @pytest.mark.parametrize("name", list(small_cases()))
 def test_fused_update_matches_oracle(ctx, name, variant):
     """both cell-kernel variants (one thread per cell with direct loads / tiled with bulk-async staging)"""
@@ -61,7 +61,7 @@ def test_fused_update_matches_oracle(ctx, name, variant):
     try:
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
     finally:
-        ctx.set_cell_kernel(1)
+        ctx.set_cell_kernel(2)
     oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
     report = {}
     compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU, P.F_U], report)
@@ -74,14 +74,15 @@ def test_tiled_kernel_capacity_fallback(ctx):
     case = cases.cfg3(base=(20, 20, 20))
     ctx.load_case(case)
     res = {}
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.set_cell_kernel(variant)
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
         res[variant] = {f: ctx.download(f) for f in case.outputs + [P.F_GRADU]}
-    ctx.set_cell_kernel(1)
+    ctx.set_cell_kernel(2)
     for f in res[0]:
-        assert np.array_equal(res[0][f][0], res[1][f][0], equal_nan=True), P.FIELD_NAMES[f]
-        assert np.array_equal(res[0][f][1], res[1][f][1], equal_nan=True), P.FIELD_NAMES[f]
+        for v in (1, 2):
+            assert np.array_equal(res[0][f][0], res[v][f][0], equal_nan=True), (v, P.FIELD_NAMES[f])
+            assert np.array_equal(res[0][f][1], res[v][f][1], equal_nan=True), (v, P.FIELD_NAMES[f])
 
 
 @pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly", "cfg4_nortonhoff"])
@@ -252,7 +253,7 @@ def _host_staged_check(ctx, case, chunks):
 def test_degenerate_meshes(ctx, dims):
     """one cell (no internal face), one row crossing a tile boundary, single layers"""
     case = cases.cfg1(dims=dims)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         ctx.load_case(case)
         ctx.set_cell_kernel(variant)
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
@@ -260,7 +261,7 @@ def test_degenerate_meshes(ctx, dims):
         compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU])
         for which in (P.ADDR_OWNER_START, P.ADDR_EXTRA_START, P.ADDR_EXTRA_FACE, P.ADDR_CELL_FACES, P.ADDR_FACE_COLOUR):
             assert ctx.addressing(which).tobytes() == oc.addressing(which).tobytes()
-    ctx.set_cell_kernel(1)
+    ctx.set_cell_kernel(2)
 
 
 @pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg3_poly"])
@@ -289,7 +290,7 @@ def test_stress_strain_post_processing(ctx, name):
     assert np.array_equal(np.concatenate([gi, gb]), oc.field(P.F_SIGMAVM))  # pure IEEE arithmetic
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["direct", "tiled"])
+@pytest.mark.parametrize("variant", [0, 1, 2], ids=["direct", "tiled", "pipe"])
 @pytest.mark.parametrize("name", ["cfg1_hex", "cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly"])
 def test_interface_correct_matches_oracle(ctx, name, variant):
     """interfaceProperties::correct() (SURVEY 8f-2): gradAlpha, nHatf, K -- pure IEEE arithmetic in the
@@ -304,7 +305,7 @@ def test_interface_correct_matches_oracle(ctx, name, variant):
     try:
         ctx.interface_correct(dn)
     finally:
-        ctx.set_cell_kernel(1)
+        ctx.set_cell_kernel(2)
     oc.interface_correct(dn)
     for f in (P.F_GRADALPHA, P.F_CURVATURE):
         gi, gb = ctx.download(f)
@@ -453,13 +454,13 @@ def test_tile_compact_layout_is_bit_identical(name):
             else:
                 assert np.array_equal(forder, np.arange(m.nInternalFaces))
             out = {}
-            for variant in (0, 1):
+            for variant in (0, 1, 2):
                 c.set_cell_kernel(variant)
                 c.update_fused(case.params, capi.FUSED_WRITE_GRAD)
                 for f in case.outputs + [P.F_GRADU, P.F_U]:
                     gi, gb = c.download(f)
                     out[(variant, f)] = np.concatenate([gi, gb])
-            c.set_cell_kernel(1)
+            c.set_cell_kernel(2)
             c.interface_correct(c.interface_delta_n())
             for f in (P.F_GRADALPHA, P.F_CURVATURE):
                 gi, gb = c.download(f)
