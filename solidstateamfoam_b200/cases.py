@@ -234,6 +234,103 @@ def cfg5_slab(rank, n_ranks, dims_per_rank=(512, 512, 32)) -> Case:
                    meta=dict(rank=rank, n_ranks=n_ranks))
 
 
+def block_grid(n_ranks: int, dims) -> tuple:
+    """(px, py, pz) with px*py*pz = n_ranks and equal blocks, minimising the processor faces of the busiest rank --
+    the structured partition a graph partitioner (scotch) finds for a box; ties go to the split with the fewest
+    cuts normal to x, then y.  512x512x256 -> 1x2x1, 2x2x1, 2x2x2 (131 072 processor faces per rank at 8 ranks,
+    SURVEY 8e)."""
+    best = None
+    for px in range(1, n_ranks + 1):
+        if n_ranks % px or dims[0] % px:
+            continue
+        for py in range(1, n_ranks // px + 1):
+            if (n_ranks // px) % py or dims[1] % py:
+                continue
+            pz = n_ranks // (px * py)
+            if dims[2] % pz:
+                continue
+            p = (px, py, pz)
+            loc = [dims[a] // p[a] for a in range(3)]
+            cut = sum(min(2, p[a] - 1) * loc[(a + 1) % 3] * loc[(a + 2) % 3] for a in range(3))
+            key = (cut, px, py)
+            if best is None or key < best[0]:
+                best = (key, p)
+    if best is None:
+        raise ValueError(f"cannot split {dims} into {n_ranks} equal blocks")
+    return best[1]
+
+
+def cfg5_part(rank: int, n_ranks: int, decomp: str = "block", dims=(512, 512, 256)) -> Case:
+    """rank's partition of the cfg5 AFSD box (BASELINE.json configs[4]: 64M cells, SheppardWright), generated
+    directly with its processor patches (no global mesh is ever built).  decomp = "block": structured blocks with up
+    to three neighbours per rank (block_grid); "slab": z-slabs (two neighbours)."""
+    seed = SEED0 + 5
+    cell = 0.25e-3
+    grid = block_grid(n_ranks, dims) if decomp == "block" else (1, 1, n_ranks)
+    if any(dims[a] % grid[a] for a in range(3)):
+        raise ValueError(f"cannot split {dims} {decomp}-wise into {n_ranks}")
+    idx = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
+    loc = tuple(dims[a] // grid[a] for a in range(3))
+
+    def rank_of(i, j, k):
+        return i + grid[0] * (j + grid[1] * k)
+
+    side = [-1] * 6
+    for a in range(3):
+        for s, d in ((0, -1), (1, +1)):
+            j = list(idx)
+            j[a] += d
+            if 0 <= j[a] < grid[a]:
+                side[2 * a + s] = rank_of(*j)
+    origin = tuple(idx[a] * loc[a] * cell for a in range(3))
+    m = _hex(loc, cell, side=tuple(side), rank=rank, origin=origin)
+    top = m.patch_id("zmax")
+    mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
+    if top >= 0 and m.patchSize[top] > 0:
+        stick = P.constant_slip_stick(top, betaTQ=0.9, delta=0.5, omega=OMEGA, muf=0.3)
+        rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
+    else:
+        stick = P.no_friction_patch(0.9)
+        rot = None
+    box = ((0.0, 0.0, 0.0), tuple(dims[a] * cell for a in range(3)))
+    return _finish("cfg5", m, _fields(m, seed + rank, "tanh", z0=0.6 * dims[2] * cell, box=box),
+                   sheppard_wright_aa6061(), mix, stick, rot, seed,
+                   meta=dict(rank=rank, n_ranks=n_ranks, decomp=decomp, grid=grid))
+
+
+def parity_parts(n_ranks: int, decomp: str):
+    """A small sheared box in n_ranks partitions for the multi-rank parity checks (tests/multigpu_parity.py and the
+    parity record of bench.py): "slab" = z-slabs generated directly, "random" = a ragged blocky cellProc list
+    (random owner per 3x3x2 brick, every pair of ranks touches) through the decomposePar stand-in."""
+    dims = (12, 10, 4 * max(n_ranks, 2))
+    cell = 0.5e-3
+    box = ((0.0, 0.0, 0.0), (dims[0] * cell, dims[1] * cell, dims[2] * cell))
+    if n_ranks == 1:
+        meshes = [M.hex_block(*dims, length=box[1], affine=(1.0, 0.2, 0.1, 0.0, 1.0, 0.15, 0.0, 0.0, 1.0))]
+    elif decomp == "slab":
+        nz = dims[2] // n_ranks
+        meshes = [M.hex_block(dims[0], dims[1], nz, (0, 0, r * nz * cell), (dims[0] * cell, dims[1] * cell, nz * cell),
+                              side_nbr_rank=tuple([-1] * 4 + [r - 1 if r > 0 else -1, r + 1 if r < n_ranks - 1 else -1]),
+                              my_rank=r) for r in range(n_ranks)]
+    else:
+        h = M.hex_block(*dims, length=box[1], affine=(1.0, 0.2, 0.1, 0.0, 1.0, 0.15, 0.0, 0.0, 1.0), _keep=True)
+        rng = np.random.default_rng(11)
+        ii, jj, kk = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij")
+        brick = (ii // 3) + 7 * (jj // 3) + 53 * (kk // 2)
+        owner_of_brick = rng.integers(0, n_ranks, size=brick.max() + 1)
+        owner_of_brick[:n_ranks] = np.arange(n_ranks)  # no empty rank
+        cp = owner_of_brick[brick].transpose(2, 1, 0).reshape(-1)
+        _, meshes = M.decompose(h, cp, n_ranks)
+    parts = []
+    for r, m in enumerate(meshes):
+        top = m.patch_id("zmax")
+        mix = P.mixture(2700.0, 1.2, 896.0, 1005.0, P.k_cubic(100.0, 0.2, -1e-4, 1e-8, 293.0, 855.0), P.k_constant(0.026))
+        stick = P.constant_slip_stick(top, 0.9, 0.5, OMEGA, 0.3)
+        rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
+        parts.append(_finish("mg", m, _fields(m, 777 + r, "tanh", box=box), sheppard_wright_aa6061(), mix, stick, rot, 777))
+    return parts
+
+
 def advance(case: Case, step: int) -> None:
     """cfg1's '10 updates with U,T advanced analytically per step' (SURVEY §8d)."""
     flds = _fields(case.mesh, case.meta["seed"], "step" if case.name == "cfg1" else "tanh", step=step)

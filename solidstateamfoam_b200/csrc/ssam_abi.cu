@@ -53,6 +53,8 @@ struct ssam_ctx {
     // self-pipelined tiles (default)
     int cellKernel = 2;
     int pipeGridCap = 0;  // > 0: cap on the persistent kernel's grid (experiments)
+    int* pipeSched = nullptr;  // 8 x {next position, CTAs done}: counters of the persistent kernel's dynamic scheduler
+    int pipeSchedNext = 0;     // launches cycle through the 8 pairs (two launches of one update may overlap)
     // cell layout: 0 = the caller's numbering, 1 = tile-compact when it pays (default), 2 = always tile-compact
     int layoutMode = 1;
     int* perm = nullptr;      // device position i holds the caller's cell perm[i] (nullptr = identity)
@@ -238,6 +240,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->extra);
     devFree(c->tileDesc);
     devFree(c->tileIota);
+    devFree(c->pipeSched);
     devFree(c->tileOrder);
     devFree(c->descInterior);
     devFree(c->descCoupled);
@@ -351,6 +354,15 @@ ssam_status buildAddressing(ssam_ctx* ctx) {
     TRY(devAlloc(ctx, &ctx->tileDesc, size_t(ctx->nTiles)));
     LAUNCH(k_tile_desc, gridFor(ctx->nTiles, 256), 256, ctx->ownerStart, ctx->extraStart, nc, ctx->nTiles,
            ctx->tileDesc);
+    {
+        int* cnt = nullptr;
+        TRY(devAlloc(ctx, &cnt, 1));
+        CU(cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
+        LAUNCH(k_count_oversize, gridFor(ctx->nTiles, 256), 256, ctx->tileDesc, ctx->nTiles, cnt);
+        CU(cudaMemcpyAsync(&ctx->nTilesOversize, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(cnt);
+    }
     {
         std::vector<int> iota(ctx->nTiles);
         for (int t = 0; t < ctx->nTiles; ++t) iota[t] = t;
@@ -792,7 +804,7 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
     return SSAM_OK;
 }
 // persistent, self-pipelined variant: one CTA per resident slot, looping over the work list
-template <int M>
+template <int M, bool FITS>
 ssam_status launchPipeOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, int count, cudaStream_t stream) {
     if (count == 0) return SSAM_OK;
     UpdateArgs a = a0;
@@ -813,35 +825,56 @@ ssam_status launchPipeOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, 
     const int smem = int(sizeof(TileSmem));
     int& slots = residentCtas[ctx->device & 63];
     if (slots == 0) {
-        CU(cudaFuncSetAttribute(k_cells_pipe<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute(k_cells_pipe<M, FITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int perSm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_cells_pipe<M>, TILE, size_t(smem)));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_cells_pipe<M, FITS>, TILE, size_t(smem)));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         CHECK(perSm > 0 && sms > 0, SSAM_ERR_CUDA, "k_cells_pipe does not fit on this device");
         slots = perSm * sms;
     }
     int grid = std::min(count, slots);
     if (ctx->pipeGridCap > 0) grid = std::min(grid, ctx->pipeGridCap);
-    // the L2 prefetch distances are given in tiles ahead of the CTA's NEXT tile
-    if (a.pfDist > 0) {
-        a.pfDist += grid;
-        a.pfDistU += grid;
+    // the persistent kernel issues a tile's copies a whole chain phase ahead of their use: the L2 prefetch that
+    // k_cells_tiled needs only adds issue work here (measured, profiles/r2_k_cells_pipe.md) -- opt-in via SSAM_PF_PIPE
+    static const int pfPipe = std::getenv("SSAM_PF_PIPE") ? std::atoi(std::getenv("SSAM_PF_PIPE")) : 0;
+    if (pfPipe > 0) {
+        a.pfDistU = pfPipe + grid + (a.pfDistU - a.pfDist);
+        a.pfDist = pfPipe + grid;
+    } else {
+        a.pfDist = a.pfDistU = 0;
     }
-    k_cells_pipe<M><<<grid, TILE, smem, stream>>>(a);
+    // SSAM_PIPE_DYNAMIC=0: static round-robin instead of the atomic work counter; SSAM_PIPE_STAGGER_NS: start stagger
+    static const int dynamicSched = std::getenv("SSAM_PIPE_DYNAMIC") ? std::atoi(std::getenv("SSAM_PIPE_DYNAMIC")) : 1;
+    static const int staggerNs = std::getenv("SSAM_PIPE_STAGGER_NS") ? std::atoi(std::getenv("SSAM_PIPE_STAGGER_NS")) : 6000;
+    a.sched = nullptr;
+    if (dynamicSched && grid < count) {
+        if (!ctx->pipeSched) {
+            TRY(devAlloc(ctx, &ctx->pipeSched, 16));
+            CU(cudaMemsetAsync(ctx->pipeSched, 0, 16 * sizeof(int), stream));
+        }
+        a.sched = ctx->pipeSched + 2 * (ctx->pipeSchedNext++ & 7);
+    }
+    a.staggerNs = grid < count ? staggerNs : 0;
+    k_cells_pipe<M, FITS><<<grid, TILE, smem, stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return SSAM_OK;
 }
 ssam_status launchCellsPipe(ssam_ctx* ctx, const UpdateArgs& a, int model1, const int* list, int count,
                             cudaStream_t stream) {
+#define SSAM_PIPE(M)                                                                         \
+    case M:                                                                                  \
+        return ctx->nTilesOversize == 0 ? launchPipeOne<M, true>(ctx, a, list, count, stream) \
+                                        : launchPipeOne<M, false>(ctx, a, list, count, stream);
     switch (model1) {
-        case SSAM_VISC_NEWTONIAN: return launchPipeOne<SSAM_VISC_NEWTONIAN>(ctx, a, list, count, stream);
-        case SSAM_VISC_SHEPPARD_WRIGHT: return launchPipeOne<SSAM_VISC_SHEPPARD_WRIGHT>(ctx, a, list, count, stream);
-        case SSAM_VISC_FKS: return launchPipeOne<SSAM_VISC_FKS>(ctx, a, list, count, stream);
-        case SSAM_VISC_NORTON_HOFF: return launchPipeOne<SSAM_VISC_NORTON_HOFF>(ctx, a, list, count, stream);
-        case TILED_GRAD: return launchPipeOne<TILED_GRAD>(ctx, a, list, count, stream);
-        case TILED_STRAIN: return launchPipeOne<TILED_STRAIN>(ctx, a, list, count, stream);
+        SSAM_PIPE(SSAM_VISC_NEWTONIAN)
+        SSAM_PIPE(SSAM_VISC_SHEPPARD_WRIGHT)
+        SSAM_PIPE(SSAM_VISC_FKS)
+        SSAM_PIPE(SSAM_VISC_NORTON_HOFF)
+        SSAM_PIPE(TILED_GRAD)
+        SSAM_PIPE(TILED_STRAIN)
     }
+#undef SSAM_PIPE
     return fail(ctx, SSAM_ERR_UNKNOWN_MODEL, "Unknown viscosityModel type");
 }
 

@@ -22,36 +22,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def build_parts(n_ranks, decomp):
     from solidstateamfoam_b200 import cases
-    from solidstateamfoam_b200 import mesh as M
-    from solidstateamfoam_b200 import params as P
 
-    dims = (12, 10, 4 * n_ranks)
-    cell = 0.5e-3
-    box = ((0.0, 0.0, 0.0), (dims[0] * cell, dims[1] * cell, dims[2] * cell))
-    if decomp == "slab":
-        meshes = [M.hex_block(dims[0], dims[1], 4, (0, 0, r * 4 * cell), (dims[0] * cell, dims[1] * cell, 4 * cell),
-                              side_nbr_rank=tuple([-1] * 4 + [r - 1 if r > 0 else -1, r + 1 if r < n_ranks - 1 else -1]),
-                              my_rank=r) for r in range(n_ranks)]
-    else:
-        h = M.hex_block(*dims, length=(dims[0] * cell, dims[1] * cell, dims[2] * cell),
-                        affine=(1.0, 0.2, 0.1, 0.0, 1.0, 0.15, 0.0, 0.0, 1.0), _keep=True)
-        rng = np.random.default_rng(11)
-        nc = dims[0] * dims[1] * dims[2]
-        # blocky random partition: random owner per 2x2x2 brick -> ragged processor patches, every pair of ranks touches
-        ii, jj, kk = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij")
-        brick = (ii // 3) + 7 * (jj // 3) + 53 * (kk // 2)
-        owner_of_brick = rng.integers(0, n_ranks, size=brick.max() + 1)
-        cp = owner_of_brick[brick].transpose(2, 1, 0).reshape(-1)
-        _, meshes = M.decompose(h, cp, n_ranks)
-    parts = []
-    for r, m in enumerate(meshes):
-        top = m.patch_id("zmax")
-        mix = P.mixture(2700.0, 1.2, 896.0, 1005.0, P.k_cubic(100.0, 0.2, -1e-4, 1e-8, 293.0, 855.0), P.k_constant(0.026))
-        stick = P.constant_slip_stick(top, 0.9, 0.5, cases.OMEGA, 0.3)
-        rot = P.constant_rotational_slip(top, cases.OMEGA, 0.5, cases.VT)
-        flds = cases._fields(m, 777 + r, "tanh", box=box)
-        parts.append(cases._finish("mg", m, flds, cases.sheppard_wright_aa6061(), mix, stick, rot, 777))
-    return parts
+    return cases.parity_parts(n_ranks, decomp)
 
 
 def main():
