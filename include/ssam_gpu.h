@@ -355,7 +355,11 @@ SSAM_API ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN);
 /* ---- fused entry point (the benchmarked path) ---------------------------------------------------
  * One pass: grad(U) -> EPSDOT -> nuModel1/2.correct() (NU1,SIGMAF,SIGMAY,NU2) -> NU -> MUEFF ->
  * QVISC,QFRIC -> RHO,CP,K.  Per-field results equal the staged calls issued in that order on the
- * same inputs.  `flags`: bit 0 also write SSAM_F_GRADU. */
+ * same inputs.  `flags` (ssam_fused_flags): SSAM_FUSED_WRITE_GRAD also writes SSAM_F_GRADU; SSAM_FUSED_HALO_INPUTS
+ * refreshes the processor-patch values of U, temp and alpha1 from the neighbour ranks before the gradient (what
+ * U.correctBoundaryConditions() does in the solver, pEqn.H:73) -- a multi-rank caller that does not exchange them
+ * itself (ssam_halo_exchange) MUST set it, otherwise the gradient reads stale halo values. */
+typedef enum { SSAM_FUSED_WRITE_GRAD = 1, SSAM_FUSED_HALO_INPUTS = 2 } ssam_fused_flags;
 SSAM_API ssam_status ssam_update_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags);
 /* Host-staged drop-in of the same update: uploads U,T,alpha1,p (AoS host buffers, internal+boundary),
  * runs the fused kernels, downloads the listed output fields. Used for the e2e metric. */
@@ -379,6 +383,10 @@ SSAM_API ssam_status ssam_set_host_chunks(ssam_ctx* ctx, int n);
  * Evaluates one of the device math routines of csrc/fastmath.cuh on host arrays (tests/test_gpu_math.py):
  * fn 0 log, 1 exp, 2 pow(x,y), 3 asinh, 4 exact division x/y, 5 operator / , 6 x/x, 7 asinh(exp(x)). */
 SSAM_API ssam_status ssam_debug_math(ssam_ctx* ctx, int fn, const double* x, const double* y, double* out, int64_t n);
+/* Measured FP64 issue ceiling of the device: thread-level FP64 instructions per second of a DFMA-only micro-kernel
+ * (8 independent chains per thread, 8 CTAs of 256 threads per SM, best of 4 timed launches, CUDA events).  The
+ * fused update is co-limited by FP64 issue; bench.py prints roofline.fp64_frac against this. */
+SSAM_API ssam_status ssam_measure_fp64_peak(ssam_ctx* ctx, double* fp64_instr_per_s);
 
 /* ---- multi-GPU: processor-patch halos over NCCL --------------------------------------------------
  * Replaces processorFvPatchField initEvaluate/evaluate (OpenFOAM, triggered by
@@ -392,8 +400,13 @@ SSAM_API ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t field_mask);
 /* Transport of the processor-patch exchanges: 1 = peer memory over NVLink (the pack kernel stores straight into the
  * neighbour's IPC-mapped receive slot and publishes a flag; the receiver waits with a stream memory operation),
  * 2 = grouped ncclSend/ncclRecv, 0 = not decided yet (before the first exchange) or no processor patches.
- * Default is NCCL (measured faster on B200/NVSwitch); SSAM_HALO=p2p in the environment selects the peer-memory path. */
+ * Default is peer memory: ssam_update_fused then runs push(U,temp,alpha1) -> interior tiles -> wait + unpack -> coupled
+ * tiles -> push(epsilonDotEq) -> wait + unpack -> boundary faces on one stream, so the halos travel while the interior
+ * tiles run and no library kernel shares the SMs with them.  SSAM_HALO=nccl in the environment selects the NCCL
+ * exchange, which is also the fallback when a neighbour's memory cannot be mapped. */
 SSAM_API int ssam_halo_transport(const ssam_ctx* ctx);
+/* Bytes this rank stored into its neighbours' memory (or sent through NCCL) during the last ssam_update_fused. */
+SSAM_API int64_t ssam_halo_bytes_last_update(const ssam_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,22 @@ def build(name):
         return cases.cfg5_slab(0, 1, (512, 512, 256))
     if name == "cfg5q":  # a quarter of the box (z): the same 512x512 planes at a quarter of the set-up time
         return cases.cfg5_slab(0, 1, (512, 512, 64))
+    if name == "cfg2sw":  # cfg2's mesh with cfg5's constitutive model: separates model cost from mesh shape
+        c = cases.cfg2()
+        c.params.visc1 = cases.sheppard_wright_aa6061()
+        return c
+    if name == "cfg5qfks":  # cfg5's planes with cfg2's model
+        c = cases.cfg5_slab(0, 1, (512, 512, 64))
+        c.params.visc1 = cases.fks_placeholder()
+        return c
+    if name == "cfg5qnh":  # ... and with NortonHoff (needs no sigmay -> no friction patch)
+        c = cases.cfg5_slab(0, 1, (512, 512, 64))
+        c.params.visc1 = cases.norton_hoff_placeholder()
+        c.params.stick.fricPatch = -1
+        c.bytes_per_update = cases.algorithmic_bytes(c.mesh, 0, True)
+        return c
+    if name == "cfg5y":  # the same 16.8M cells as 256 x 512 x 128: is it the plane size?
+        return cases.cfg5_part(0, 1, "block", dims=(256, 512, 128))
     raise SystemExit(name)
 
 

@@ -25,7 +25,7 @@ SYMBOLS = [
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_div_dev_rho_reff_explicit", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
     "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
-    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange", "ssam_halo_transport",
+    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_measure_fp64_peak", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange", "ssam_halo_transport", "ssam_halo_bytes_last_update",
 ]
 
 
@@ -104,10 +104,13 @@ def load():
     L.ssam_update_fused_host.argtypes = [vp, C.POINTER(P.UpdateParams), C.POINTER(P.HostIO)]
     L.ssam_set_host_chunks.argtypes = [vp, C.c_int]
     L.ssam_debug_math.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int64]
+    L.ssam_measure_fp64_peak.argtypes = [vp, dp]
     L.ssam_comm_unique_id.argtypes = [vp]
     L.ssam_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ssam_halo_exchange.argtypes = [vp, C.c_uint32]
     L.ssam_halo_transport.argtypes = [vp]
+    L.ssam_halo_bytes_last_update.argtypes = [vp]
+    L.ssam_halo_bytes_last_update.restype = C.c_int64
     _lib = L
     return L
 
@@ -190,6 +193,10 @@ class Context:
 
     def halo_transport(self) -> str:
         return {0: "none", 1: "peer-memory", 2: "nccl"}[self.L.ssam_halo_transport(self.h)]
+
+    def halo_bytes_per_update(self) -> int:
+        """bytes this rank sent to its neighbours during the last fused update"""
+        return int(self.L.ssam_halo_bytes_last_update(self.h))
 
     def set_cell_layout(self, mode: int):
         """0 = caller's cell order, 1 = tile-compact when it pays (default), 2 = always; before mesh_set"""
@@ -336,6 +343,12 @@ class Context:
 
     def update_fused_host(self, p: P.UpdateParams, io: P.HostIO):
         self._chk(self.L.ssam_update_fused_host(self.h, C.byref(p), C.byref(io)))
+
+    def fp64_peak(self) -> float:
+        """measured FP64 issue ceiling, thread-level FP64 instructions per second (DFMA-only micro-kernel)"""
+        v = C.c_double()
+        self._chk(self.L.ssam_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     def debug_math(self, fn: int, x, y=None) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -61,7 +61,6 @@ struct ViscDerived {
     double mu0OverRho;  // mu0_/rho_                              NortonHoff.C:60
     double mMinus1;     // m_ - 1                                 NortonHoff.C:63
     double sqrt3;       // sqrt(3.0)                              NortonHoff.C:62
-    double invTmTa;     // 1/(Tm_ - Ta_): Th = (Tlim - Ta)*invTmTa differs from the quotient by <= 1 ulp
     double invE0;       // 1/e0_
     int b2IsOne;        // pow(x, 1.0) == x exactly
     int invC2IsOne;
@@ -91,13 +90,17 @@ SSAM_DEV ViscOut sheppardWright(const ssam_viscosity_params& p, const ViscDerive
 SSAM_DEV ViscOut fks(const ssam_viscosity_params& p, const ViscDerived& d, double T, double e) {
     ViscOut o;
     const double Tlim = ofMin(ofMax(T, p.Ta), p.Tm);                      // :108
-    const double Th = (Tlim - p.Ta) * d.invTmTa;                          // :112
+    // :112  true quotient: Th feeds exp(-c1*Th) under the 1 - 1/z cancellation below, where a 1-ulp difference in
+    // Th is amplified by c1*Th/Theta (DESIGN.md 7 "conditioning")
+    const double Th = divExact(Tlim - p.Ta, d.TmTa);
     const double H = d.Hcoef * selfRatio(T);                              // :73  (X*T)/T: X to 1 ulp, NaN at T = 0
     const double base = Th + kSMALL;
     const double pw = p.b1 * (d.b2IsOne ? base : fastPow(base, p.b2));    // :89 / :152
     const double Lam = 1.0 + pw * (p.b3 * fastLog(e * d.invE0 + kVSMALL));  // :89
     const double z = 1.0 + fastExp(d.negC1 * Th);                         // in (1, 2]
-    const double Theta = 1.0 - divFast(1.0, d.invC2IsOne ? z : fastPow(z, d.invC2));  // :99
+    // :99  1.0 - 1.0/pow(z, 1/c2) cancels as exp(-c1*Th) -> 0 (T -> Tm, large c1): the quotient is the IEEE one, so
+    // that with c2 = 1 Theta carries the reference's own bits whenever exp() rounds z = 1 + e the same way
+    const double Theta = 1.0 - divExact(1.0, d.invC2IsOne ? z : fastPow(z, d.invC2));
     o.sigmaf = (H * Lam) * Theta;                                         // :129
     o.sigmay = (p.a1 * Theta) * (1.0 + pw * d.b3LogY);                    // :152
     o.nu = ofMax(p.nuMin, ofMin(p.nuMax, divFast(o.sigmaf, d.threeRho * ofMax(e, p.eDotMin))));  // :172-181

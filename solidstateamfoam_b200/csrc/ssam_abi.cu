@@ -110,8 +110,10 @@ struct ssam_ctx {
         unsigned long long seq = 0;
     } p2p;
 
+    size_t haloBytesLastUpdate = 0;  // bytes this rank sent to its neighbours during the last fused update
     // optional per-kernel timing (ssam_profile_enable)
     bool profile = false;
+    int64_t profUpdates = 0;  // fused updates covered by profEvents (an update may contribute several event pairs)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
 
     // lazily built integer tables
@@ -474,7 +476,6 @@ ViscDerived deriveVisc(const ssam_viscosity_params& p) {
     d.mu0OverRho = p.mu0 / p.rho;
     d.mMinus1 = p.m - 1;
     d.sqrt3 = std::sqrt(3.0);
-    d.invTmTa = 1.0 / d.TmTa;
     d.invE0 = 1.0 / p.e0;
     d.b2IsOne = (p.b2 == 1.0) ? 1 : 0;
     d.invC2IsOne = (d.invC2 == 1.0) ? 1 : 0;
@@ -535,10 +536,12 @@ StreamWaitValue64Fn streamWaitValue64() {
 ssam_status p2pSetup(ssam_ctx* ctx) {
     auto& P = ctx->p2p;
     P.state = -1;
-    // measured on 2 B200s (profiles/r1_scaling.md): the NCCL exchange is 12 us per step faster than this path, so
-    // NCCL is the default and the peer-memory path is opt-in (SSAM_HALO=p2p)
+    // Round 1 ran both exchanges on a second stream beside the interior tiles; there NCCL was 12 us per step faster
+    // (profiles/r1_scaling.md).  The round-2 schedule (updateFusedAsync) keeps the whole step on one stream and only
+    // needs push / wait-flag / unpack pieces, which NCCL's send/recv pairs cannot be split into: peer memory is the
+    // default, SSAM_HALO=nccl selects the NCCL exchange (also the fallback when a neighbour cannot be mapped).
     const char* env = std::getenv("SSAM_HALO");
-    int ok = (env && std::string(env) == "p2p") ? 1 : 0;
+    int ok = (env && std::string(env) == "nccl") ? 0 : 1;
     if (!streamWaitValue64()) ok = 0;
     NcclApi& N = nccl();
     const int nP = ctx->nProcPatches;
@@ -622,7 +625,9 @@ ssam_status p2pSetup(ssam_ctx* ctx) {
     return SSAM_OK;
 }
 
-ssam_status haloExchangePeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStream_t stream) {
+// push: gather field[faceCells] of every processor patch and store each run straight into the neighbour's receive slot
+// over NVLink; the last CTA publishes the exchange number into the neighbours' flag words.  Returns that number.
+ssam_status haloPushPeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStream_t stream, unsigned long long* seqOut) {
     auto& P = ctx->p2p;
     const unsigned long long seq = ++P.seq;
     const size_t slot = size_t(seq & 1ull);
@@ -640,6 +645,15 @@ ssam_status haloExchangePeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStr
     k_halo_pack_peer<<<grid, 256, 0, stream>>>(ctx->haloSendCells, L, nc, pl, P.done, seq);
     ctx->launches++;
     CU(cudaGetLastError());
+    ctx->haloBytesLastUpdate += size_t(ctx->nProcFaces) * size_t(nc) * sizeof(double);
+    *seqOut = seq;
+    return SSAM_OK;
+}
+// wait (stream memory operation, no spinning CTA) until every neighbour has published exchange `seq`, then move the
+// received runs into the boundary part of the planes
+ssam_status haloWaitUnpackPeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, unsigned long long seq, cudaStream_t stream) {
+    auto& P = ctx->p2p;
+    const size_t slot = size_t(seq & 1ull);
     StreamWaitValue64Fn wait = streamWaitValue64();
     for (int p = 0; p < ctx->nProcPatches; ++p) {
         const int peer = ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(p)])];
@@ -653,23 +667,29 @@ ssam_status haloExchangePeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStr
     HaloLayout H;
     H.nPatches = ctx->nProcPatches;
     for (int p = 0; p <= ctx->nProcPatches; ++p) H.offsets[p] = ctx->haloOffsets[size_t(p)];
+    const int grid = gridFor((long long)ctx->nProcFaces * nc, 256);
     k_halo_unpack<<<grid, 256, 0, stream>>>(P.recvBuf + 32 + slot * P.slotDoubles, H, nc, pl, ctx->nCells, P.patchB0);
     ctx->launches++;
     CU(cudaGetLastError());
     return SSAM_OK;
 }
+ssam_status haloExchangePeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStream_t stream) {
+    unsigned long long seq = 0;
+    TRY(haloPushPeer(ctx, pl, nc, stream, &seq));
+    return haloWaitUnpackPeer(ctx, pl, nc, seq, stream);
+}
 
-ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cudaStream_t stream) {
-    if (ctx->nProcPatches == 0 || nFields == 0) return SSAM_OK;
+// collective, once per mesh: choose the halo transport (peer memory when every rank can map its neighbours)
+ssam_status ensureHaloTransport(ssam_ctx* ctx) {
+    if (ctx->nProcPatches == 0 || ctx->p2p.state != 0) return SSAM_OK;
     CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
-    if (ctx->p2p.state == 0) {
-        // collective: every rank reaches its first exchange in the same call
-        CU(cudaStreamSynchronize(ctx->stream));
-        if (ctx->commStream) CU(cudaStreamSynchronize(ctx->commStream));
-        TRY(p2pSetup(ctx));
-    }
-    PlanePtrs pl;
-    int nc = 0;
+    // every rank reaches its first exchange in the same call
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->commStream) CU(cudaStreamSynchronize(ctx->commStream));
+    return p2pSetup(ctx);
+}
+ssam_status planesOf(ssam_ctx* ctx, const int* fields, int nFields, PlanePtrs& pl, int& nc) {
+    nc = 0;
     for (int i = 0; i < nFields; ++i) {
         TRY(ensureField(ctx, fields[i]));
         for (int k = 0; k < ncompOf(fields[i]); ++k) {
@@ -678,6 +698,16 @@ ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cu
         }
     }
     for (int k = nc; k < 16; ++k) pl.p[k] = nullptr;
+    return SSAM_OK;
+}
+
+ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cudaStream_t stream) {
+    if (ctx->nProcPatches == 0 || nFields == 0) return SSAM_OK;
+    CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
+    TRY(ensureHaloTransport(ctx));
+    PlanePtrs pl;
+    int nc = 0;
+    TRY(planesOf(ctx, fields, nFields, pl, nc));
     if (ctx->p2p.state == 1) return haloExchangePeer(ctx, pl, nc, stream);
     const size_t needBuf = size_t(ctx->nProcFaces) * 16;
     if (ctx->sendCap < needBuf) {
@@ -708,6 +738,7 @@ ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cu
     }
     NC(N.GroupEnd());
     ctx->launches++;  // one fused NCCL p2p kernel per group
+    ctx->haloBytesLastUpdate += size_t(ctx->nProcFaces) * size_t(nc) * sizeof(double);
     return SSAM_OK;
 }
 ssam_status haloExchangeField(ssam_ctx* ctx, int field) { return haloExchangeFields(ctx, &field, 1, ctx->stream); }
@@ -976,6 +1007,8 @@ ssam_status buildTileOrder(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     devFree(ctx->tileOrder);
     const long long reuseBytes = (long long)ctx->bandwidthTiles * TILE * 270;
     if (reuseBytes < (40ll << 20) || ctx->nTiles < 4) return SSAM_OK;  // natural order already fits L2
+    static const int bfs = std::getenv("SSAM_BFS_ORDER") ? std::atoi(std::getenv("SSAM_BFS_ORDER")) : 1;
+    if (!bfs) return SSAM_OK;
     const int nT = ctx->nTiles;
     std::vector<std::vector<int>> adj(nT);
     for (int f = 0; f < m->nInternalFaces; ++f) {
@@ -1345,8 +1378,9 @@ ssam_status ssam_profile_get(ssam_ctx* ctx, double* ms, int64_t* n) {
         cudaEventDestroy(pr.second);
     }
     *ms = total;
-    *n = int64_t(ctx->profEvents.size());
+    *n = ctx->profUpdates > 0 ? ctx->profUpdates : int64_t(ctx->profEvents.size());
     ctx->profEvents.clear();
+    ctx->profUpdates = 0;
     return SSAM_OK;
 }
 
@@ -2172,13 +2206,22 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         ctx->nu2Filled = true;
         ctx->nu2FilledWith = p->visc2.nu;
     }
-    // Multi-GPU schedule (tiled kernel):
-    //   main stream: interior tiles ------------------------------------------.
-    //   comm stream: pack + NCCL(U,temp,alpha1) -> coupled tiles -> pack + NCCL(epsilonDotEq[,...]) -+-> boundary faces
-    // so both halo exchanges and the tiles that need them hide behind the interior tiles.
+    // Multi-GPU schedules (tiled kernels).  The tiles are split into "interior" ones and "coupled" ones (a
+    // cell of the tile has a processor face, so its gradient needs the neighbour rank's U).
+    //  (a) peer memory (default), everything on ONE stream:
+    //        push(U,temp,alpha1) -> interior tiles -> wait flags + unpack -> coupled tiles -> push(epsilonDotEq[,..])
+    //        -> wait flags + unpack -> boundary faces
+    //      push = one small kernel storing straight into the neighbours' IPC-mapped receive slots over NVLink and
+    //      publishing a flag; wait = a stream memory operation.  The neighbours' values travel while the interior
+    //      tiles (75-99 % of the step) run, no library kernel shares the SMs with them, and a rank blocks only when
+    //      a neighbour is really behind by more than that.
+    //  (b) NCCL (SSAM_HALO=nccl or a neighbour that cannot be mapped): round-1 schedule, exchanges and coupled tiles
+    //      on a high-priority second stream beside the interior tiles.
     const bool haloInputs = ctx->nProcPatches && (flags & 2);
     const bool split = ctx->nProcPatches > 0 && ctx->cellKernel >= 1;
-    if (ctx->nProcPatches && !ctx->commStream) {
+    if (ctx->nProcPatches) TRY(ensureHaloTransport(ctx));
+    const bool peer = split && ctx->p2p.state == 1;
+    if (split && !peer && !ctx->commStream) {
         // highest priority: the comm stream's small kernels must get SM slots as soon as CTAs of the
         // interior-tile kernel retire, not after its whole grid has been dispatched
         int prLo = 0, prHi = 0;
@@ -2192,35 +2235,62 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     if (model1 == SSAM_VISC_NORTON_HOFF) outs2[n2++] = SSAM_F_STRAINRATE;
     if (flags & 1) outs2[n2++] = SSAM_F_GRADU;
     const int ins[3] = {SSAM_F_U, SSAM_F_T, SSAM_F_ALPHA1};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (ctx->profile) {
-        CU(cudaEventCreate(&ev0));
-        CU(cudaEventCreate(&ev1));
-        CU(cudaEventRecord(ev0, ctx->stream));
-    }
-    if (split) {
-        CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->commStream, ctx->evMainToComm, 0));
-        if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->commStream));
+    ctx->haloBytesLastUpdate = 0;
+    // profiling: CUDA events around every tile-kernel launch of this update (their sum = the cell kernel's time)
+    auto profBegin = [&](cudaEvent_t& e0) -> ssam_status {
+        e0 = nullptr;
+        if (!ctx->profile) return SSAM_OK;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventRecord(e0, ctx->stream));
+        return SSAM_OK;
+    };
+    auto profEnd = [&](cudaEvent_t e0) -> ssam_status {
+        if (!e0) return SSAM_OK;
+        cudaEvent_t e1 = nullptr;
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e1, ctx->stream));
+        ctx->profEvents.emplace_back(e0, e1);
+        return SSAM_OK;
+    };
+    auto launchInterior = [&]() -> ssam_status {
         if (ctx->interiorRange0 >= 0) {
             UpdateArgs ar = a;
             ar.tileOffset = ctx->interiorRange0;
-            TRY(launchCellsTiled(ctx, ar, model1, nullptr, ctx->nTilesInterior, ctx->stream));
-        } else {
-            TRY(launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream));
+            return launchCellsTiled(ctx, ar, model1, nullptr, ctx->nTilesInterior, ctx->stream);
         }
-        static const bool profInterior = std::getenv("SSAM_PROFILE_INTERIOR") != nullptr;  // experiments only
-        if (ctx->profile && profInterior && ev1) {
-            CU(cudaEventRecord(ev1, ctx->stream));
-            ctx->profEvents.emplace_back(ev0, ev1);
-            ev0 = ev1 = nullptr;
-        }
+        return launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream);
+    };
+    cudaEvent_t pe = nullptr;
+    if (peer) {
+        PlanePtrs plIn, plOut;
+        int ncIn = 0, ncOut = 0;
+        TRY(planesOf(ctx, ins, 3, plIn, ncIn));
+        TRY(planesOf(ctx, outs2, n2, plOut, ncOut));
+        unsigned long long seqIn = 0, seqOut = 0;
+        if (haloInputs) TRY(haloPushPeer(ctx, plIn, ncIn, ctx->stream, &seqIn));
+        TRY(profBegin(pe));
+        TRY(launchInterior());
+        TRY(profEnd(pe));
+        if (haloInputs) TRY(haloWaitUnpackPeer(ctx, plIn, ncIn, seqIn, ctx->stream));
+        TRY(profBegin(pe));
+        TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->stream));
+        TRY(profEnd(pe));
+        TRY(haloPushPeer(ctx, plOut, ncOut, ctx->stream, &seqOut));
+        TRY(haloWaitUnpackPeer(ctx, plOut, ncOut, seqOut, ctx->stream));
+    } else if (split) {
+        TRY(profBegin(pe));
+        CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->commStream, ctx->evMainToComm, 0));
+        if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->commStream));
+        TRY(launchInterior());
         TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->commStream));
         TRY(haloExchangeFields(ctx, outs2, n2, ctx->commStream));
         CU(cudaEventRecord(ctx->evCommToMain, ctx->commStream));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->evCommToMain, 0));
+        TRY(profEnd(pe));
     } else {
         if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->stream));
+        TRY(profBegin(pe));
         if (plan) {
             for (int k = 0; k < plan->nChunks; ++k) {
                 const int t0 = k * plan->tilesPerChunk, t1 = std::min(ctx->nTiles, t0 + plan->tilesPerChunk);
@@ -2234,12 +2304,10 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         } else {
             TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, false)));
         }
+        TRY(profEnd(pe));
         if (ctx->nProcPatches) TRY(haloExchangeFields(ctx, outs2, n2, ctx->stream));
     }
-    if (ctx->profile && ev1) {
-        CU(cudaEventRecord(ev1, ctx->stream));
-        ctx->profEvents.emplace_back(ev0, ev1);
-    }
+    if (ctx->profile) ctx->profUpdates++;
     TRY((launchCellsBoundary<MODE_FUSED>(ctx, a, model1, true)));
     for (int f : outs) ctx->isSet[f] = true;
     if (hasSigma) ctx->isSet[SSAM_F_SIGMAF] = ctx->isSet[SSAM_F_SIGMAY] = true;
@@ -2501,6 +2569,36 @@ ssam_status ssam_debug_math(ssam_ctx* ctx, int fn, const double* x, const double
     return SSAM_OK;
 }
 
+// ---- FP64 issue ceiling ------------------------------------------------------------------------------------------------
+ssam_status ssam_measure_fp64_peak(ssam_ctx* ctx, double* fp64_instr_per_s) {
+    CHECK(ctx && fp64_instr_per_s, SSAM_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int grid = sms * 8, block = 256, iters = 1 << 15;
+    double* out = nullptr;
+    TRY(devAlloc(ctx, &out, size_t(grid) * block));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {  // the first repetition is the warm-up
+        CU(cudaEventRecord(e0, ctx->stream));
+        k_fp64_peak<<<grid, block, 0, ctx->stream>>>(iters, 1.0 + rep, out);
+        ctx->launches++;
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *fp64_instr_per_s = double(grid) * block * double(iters) * 8.0 / (double(best) * 1e-3);
+    return SSAM_OK;
+}
+
 // ---- comm -----------------------------------------------------------------------------------------------------
 ssam_status ssam_comm_unique_id(void* id_out) {
     ssam_ctx* ctx = nullptr;
@@ -2527,6 +2625,8 @@ ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int nRanks) 
     ctx->fricPatchCached = -1;
     return SSAM_OK;
 }
+
+int64_t ssam_halo_bytes_last_update(const ssam_ctx* ctx) { return ctx ? int64_t(ctx->haloBytesLastUpdate) : 0; }
 
 int ssam_halo_transport(const ssam_ctx* ctx) {
     if (!ctx || ctx->nProcPatches == 0 || ctx->p2p.state == 0) return 0;

@@ -115,3 +115,60 @@ def test_reader_errors(tmp_path):
     with pytest.raises(M.FoamIOError) as e:
         M.MeshHandle(M.poly_refined(4, 4, 4, _keep=True)).write_polymesh(str(tmp_path / "x"))
     assert "no point/face topology" in str(e.value)
+
+
+# ---- hand-written OpenFOAM-v1806-style files (tests/golden/foam_v1806_2cell) ----------------------------------------
+# Two unit cubes side by side, written the way v1806's own writers lay the files out (banner, `note` entry, `inGroups`,
+# one-line short lists `1(1)`, `0()`, an empty physical patch kept by decomposePar, `nonuniform 0()`), NOT by this
+# repo's writer; the expected numbers below are worked out by hand.
+FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "foam_v1806_2cell")
+
+
+def test_reads_hand_written_v1806_polymesh():
+    m = M.read_polymesh(os.path.join(FIX, "constant", "polyMesh")).mesh()
+    assert (m.nCells, m.nInternalFaces, m.nFaces) == (2, 1, 11)
+    assert m.patchName == ["left", "right", "walls"]
+    assert list(m.patchStart) == [1, 2, 3] and list(m.patchSize) == [1, 1, 8] and list(m.patchKind) == [0, 0, 0]
+    assert list(m.owner) == [0, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1] and list(m.neighbour) == [1]
+    assert np.allclose(m.V, [1.0, 1.0], rtol=1e-15)
+    assert np.allclose(m.C, [[0.5, 0.5, 0.5], [1.5, 0.5, 0.5]], rtol=1e-15)
+    expect_sf = np.array([[1, 0, 0], [-1, 0, 0], [1, 0, 0], [0, -1, 0], [0, -1, 0], [0, 1, 0], [0, 1, 0], [0, 0, -1],
+                          [0, 0, -1], [0, 0, 1], [0, 0, 1]], dtype=float)
+    assert np.allclose(m.Sf, expect_sf, atol=1e-15)
+    assert np.allclose(m.Cf[0], [1.0, 0.5, 0.5]) and np.allclose(m.Cf[2], [2.0, 0.5, 0.5])
+    assert m.weights[0] == pytest.approx(0.5, rel=1e-15) and np.all(m.weights[1:] == 1.0)
+    assert m.deltaCoeffs[0] == pytest.approx(1.0, rel=1e-15)          # 1/|C_N - C_P|
+    assert np.allclose(m.deltaCoeffs[1:], 2.0, rtol=1e-15)              # 1/|Cf - C_P| on the boundary
+
+
+def test_reads_hand_written_v1806_fields():
+    h = M.read_polymesh(os.path.join(FIX, "constant", "polyMesh"))
+    ti, tb, bc = h.read_field(os.path.join(FIX, "0", "temp"), 1)
+    assert list(ti) == [300.0, 400.0]
+    assert tb[0] == 293.0                      # fixedValue
+    assert tb[1] == 400.0                      # zeroGradient on `right`: the adjacent cell's value
+    assert list(tb[2:]) == [300.0, 400.0] * 4  # zeroGradient walls, faces alternate between the two cells
+    assert list(bc) == [P.BC_VALUE, P.BC_ZERO_GRADIENT, P.BC_ZERO_GRADIENT]
+    ui, ub, ubc = h.read_field(os.path.join(FIX, "0", "U"), 3)
+    assert np.array_equal(ui, [[1, 0, 0], [2, 0.5, 0]])
+    assert np.array_equal(ub[0], [1, 0, 0]) and np.array_equal(ub[1], [2, 0.5, 0])
+    assert np.array_equal(ub[2:], np.zeros((8, 3)))  # noSlip = fixedValue (0 0 0)
+    assert list(ubc) == [P.BC_VALUE, P.BC_ZERO_GRADIENT, P.BC_VALUE]
+
+
+def test_reads_hand_written_v1806_decomposed_case():
+    hs = M.read_decomposed_case(FIX, 2)
+    for r, h in enumerate(hs):
+        m = h.mesh()
+        assert (m.nCells, m.nInternalFaces, m.nFaces) == (1, 0, 6)
+        assert m.patchName == ["left", "right", "walls", f"procBoundary{r}to{1 - r}"]
+        assert list(m.patchKind) == [0, 0, 0, 1] and m.patchNbrRank[3] == 1 - r
+        assert list(m.patchSize) == ([1, 0, 4, 1] if r == 0 else [0, 1, 4, 1])
+        f = 5  # the processor face
+        assert np.allclose(m.Sf[f], [1.0 if r == 0 else -1.0, 0, 0], atol=1e-15)
+        # completed from the neighbour side, like processorFvPatch::makeWeights / makeDeltaCoeffs
+        assert m.weights[f] == pytest.approx(0.5, rel=1e-15)
+        assert m.deltaCoeffs[f] == pytest.approx(1.0, rel=1e-15)
+        ti, tb, bc = h.read_field(os.path.join(FIX, f"processor{r}", "0", "temp"), 1)
+        assert list(ti) == [(300.0, 400.0)[r]]
+        assert tb[-1] == (400.0, 300.0)[r]     # processor patch: the neighbour cell's value as written
