@@ -16,7 +16,7 @@ Contract (one JSON line on stdout from rank 0):
   * parity = before anything is timed, every rank runs a small decomposed case (slab and ragged random partitions)
     through the same entry points and compares its partition with the multi-rank CPU oracle: integer halo maps and
     grad U / strain rate bit-exact, every other field <= 1e-11; a mismatch fails the run;
-  * roofline = the dominant kernel (k_cells_pipe) timed live with its own CUDA events inside the library
+  * roofline = the dominant kernel (k_cells_tiled) timed live with its own CUDA events inside the library
     (ssam_profile_*), algorithmic bytes = 40*N_if + 52*N_bf + 128*N_c (SURVEY.md 8d; DESIGN.md 4);
   * e2e = the same update through ssam_update_fused_host with pinned HOST buffers on the SAME context: H2D of U,
     temp, alpha1, p and D2H of the fields the solver consumes each step inside the timed region;
@@ -617,8 +617,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra_workloads list (N=1)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity record (experiments only)")
-    ap.add_argument("--cell-kernel", type=int, default=2, choices=[0, 1, 2],
-                    help="2 = persistent self-pipelined tiles (default); 1 = tiled, one CTA per tile; 0 = one thread per "
+    ap.add_argument("--cell-kernel", type=int, default=1, choices=[0, 1, 2],
+                    help="1 = tiled, one CTA per tile (default); 2 = persistent self-pipelined tiles; 0 = one thread per "
                          "cell, direct loads")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -198,10 +198,10 @@ SSAM_API ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking);
 SSAM_API int ssam_abi_version(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 SSAM_API int64_t ssam_launch_count(const ssam_ctx* ctx);
-/* Fused cell-kernel variant: 2 (default) = persistent self-pipelined tiles (the bulk copies of a CTA's next tile
- * land while it runs the FP64 chain of the current one); 1 = tiled, one CTA per tile: inputs of 256 consecutive
- * cells staged in shared memory by 1-D bulk async copies; 0 = one thread per cell with direct global loads.
- * Results are bit-identical. */
+/* Fused cell-kernel variant: 1 (default) = tiled, one CTA per tile: inputs of 256 consecutive cells staged in shared
+ * memory by 1-D bulk async copies; 2 = persistent self-pipelined tiles (the bulk copies of a CTA's next tile land
+ * while it runs the FP64 chain of the current one; dynamic tile scheduling) -- measured slower than 1 on B200, kept
+ * as an option; 0 = one thread per cell with direct global loads.  Results are bit-identical. */
 SSAM_API ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant);
 /* Cell layout of the device planes, to be chosen before ssam_mesh_set:
  *   SSAM_LAYOUT_CALLER  (0) the caller's cell numbering;
@@ -397,6 +397,14 @@ SSAM_API ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int
 /* boundary values on processor patches <- neighbour rank's adjacent cell values, for every field
  * whose bit (1<<SSAM_F_*) is set in field_mask */
 SSAM_API ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t field_mask);
+/* In-process rank group: all `nRanks` contexts live in THIS process (on one GPU or on several with peer access);
+ * context r becomes rank r.  Same peer-memory exchange as across processes, the receive slots being linked by plain
+ * device pointers; waits are stream memory operations (no kernel ever spins on another rank), so the ranks may share
+ * one GPU.  The caller must issue each collective step (ssam_update_fused, ssam_halo_exchange, ...) on EVERY context
+ * with ssam_set_blocking(ctx, 0) before synchronising any of them -- a blocking call on one rank would wait for a
+ * neighbour whose work has not been enqueued yet.  Used by the single-GPU multi-rank parity tests and by solvers that
+ * drive several regions / partitions from one process. */
+SSAM_API ssam_status ssam_comm_init_local(ssam_ctx** ctxs, int nRanks);
 /* Transport of the processor-patch exchanges: 1 = peer memory over NVLink (the pack kernel stores straight into the
  * neighbour's IPC-mapped receive slot and publishes a flag; the receiver waits with a stream memory operation),
  * 2 = grouped ncclSend/ncclRecv, 0 = not decided yet (before the first exchange) or no processor patches.

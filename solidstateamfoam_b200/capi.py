@@ -25,7 +25,7 @@ SYMBOLS = [
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_div_dev_rho_reff_explicit", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
     "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
-    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_measure_fp64_peak", "ssam_comm_unique_id", "ssam_comm_init", "ssam_halo_exchange", "ssam_halo_transport", "ssam_halo_bytes_last_update",
+    "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_measure_fp64_peak", "ssam_comm_unique_id", "ssam_comm_init", "ssam_comm_init_local", "ssam_halo_exchange", "ssam_halo_transport", "ssam_halo_bytes_last_update",
 ]
 
 
@@ -107,6 +107,7 @@ def load():
     L.ssam_measure_fp64_peak.argtypes = [vp, dp]
     L.ssam_comm_unique_id.argtypes = [vp]
     L.ssam_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ssam_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
     L.ssam_halo_exchange.argtypes = [vp, C.c_uint32]
     L.ssam_halo_transport.argtypes = [vp]
     L.ssam_halo_bytes_last_update.argtypes = [vp]
@@ -371,6 +372,15 @@ class Context:
         buf = C.create_string_buffer(uid, P.UNIQUE_ID_BYTES)
         self._keep.append(buf)
         self._chk(self.L.ssam_comm_init(self.h, buf, rank, n_ranks))
+
+    @staticmethod
+    def comm_init_local(ctxs):
+        """link contexts of this process into one rank group (context r = rank r)"""
+        L = load()
+        arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        st = L.ssam_comm_init_local(arr, len(ctxs))
+        if st != 0:
+            raise SsamError(st, L.ssam_last_error(None).decode())
 
     def halo_exchange(self, fields):
         mask = 0

@@ -47,11 +47,14 @@ struct ssam_ctx {
     cudaEvent_t evMainToComm = nullptr, evCommToMain = nullptr;
     int pfDist = 148;    // L2 prefetch distance of the tiled kernel, in tiles (measured optimum, profiles/)
     int bandwidthTiles = 0;  // ceil(max(neighbour - owner) / TILE)
+    // 97th percentile of the tile distance of the internal faces: where the HEAVY forward neighbours sit (a tile order
+    // may put a few light neighbours very far away; prefetching towards those would only waste DRAM traffic)
+    int pfBandwidthTiles = 0;
     int hostChunks = -1;  // >= 0 overrides the chunk count of the host-staged pipeline (0/1 = unpipelined)
     int nTilesOversize = 0;
-    // 0 = one thread per cell, direct loads; 1 = tiled, bulk-async staged, one CTA per tile; 2 = persistent
-    // self-pipelined tiles (default)
-    int cellKernel = 2;
+    // 0 = one thread per cell, direct loads; 1 (default) = tiled, bulk-async staged, one CTA per tile; 2 = persistent
+    // self-pipelined tiles (round-2 experiment: slower than 1 on every workload, profiles/r2_k_cells_pipe.md)
+    int cellKernel = 1;
     int pipeGridCap = 0;  // > 0: cap on the persistent kernel's grid (experiments)
     int* pipeSched = nullptr;  // 8 x {next position, CTAs done}: counters of the persistent kernel's dynamic scheduler
     int pipeSchedNext = 0;     // launches cycle through the 8 pairs (two launches of one update may overlap)
@@ -83,6 +86,7 @@ struct ssam_ctx {
     size_t stageCap = 0;
 
     int fricPatchCached = -1;
+    int fricLocalFor = -1;  // in-process group: patch whose LOCAL sums fricSums[0..3] currently hold
     double* fricSums = nullptr;  // device: [0..3] local sums, [4..7] cross-rank sums
     int qfricZeroedFor = -2;
     bool nu2Filled = false;
@@ -97,6 +101,9 @@ struct ssam_ctx {
     size_t sendCap = 0;
     ncclComm_t comm = nullptr;
     int rank = 0, nRanks = 1;
+    // in-process rank group (ssam_comm_init_local): every rank is a context of THIS process; halo slots are linked by
+    // plain device pointers instead of IPC handles, the small reductions go through the host
+    std::vector<ssam_ctx*> localPeers;
     // halo exchange over peer memory (IPC-mapped receive slots); NCCL stays the fallback
     struct P2P {
         int state = 0;  // 0 = not tried, 1 = on, -1 = unavailable (NCCL path)
@@ -280,6 +287,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->cellFaces);
     devFree(c->faceColour);
     c->fricPatchCached = -1;
+    c->fricLocalFor = -1;
     c->qfricZeroedFor = -2;
     c->nu2Filled = false;
     c->haveMesh = false;
@@ -680,8 +688,84 @@ ssam_status haloExchangePeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStr
 }
 
 // collective, once per mesh: choose the halo transport (peer memory when every rank can map its neighbours)
+// ---- in-process rank group -------------------------------------------------------------------------------------------
+// own receive buffer, completion counter and patch table (what p2pSetup allocates before its handshake)
+ssam_status p2pAllocOwn(ssam_ctx* ctx) {
+    auto& P = ctx->p2p;
+    if (P.recvBuf) return SSAM_OK;
+    CU(cudaSetDevice(ctx->device));
+    const int nP = ctx->nProcPatches;
+    P.slotDoubles = size_t(ctx->nProcFaces) * 16;
+    const size_t total = 32 + 2 * P.slotDoubles;
+    TRY(devAlloc(ctx, &P.recvBuf, total));
+    CU(cudaMemset(P.recvBuf, 0, total * sizeof(double)));
+    TRY(devAlloc(ctx, &P.done, 1));
+    CU(cudaMemset(P.done, 0, sizeof(unsigned)));
+    std::vector<int> b0(size_t(nP) + 1, 0);
+    for (int p = 0; p < nP; ++p) b0[size_t(p)] = ctx->patchStart[size_t(ctx->haloPatch[size_t(p)])] - ctx->nIF;
+    TRY(devAlloc(ctx, &P.patchB0, size_t(nP) + 1));
+    CU(cudaMemcpy(P.patchB0, b0.data(), (size_t(nP) + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    return SSAM_OK;
+}
+ssam_status p2pSetupLocal(ssam_ctx* ctx) {
+    auto& P = ctx->p2p;
+    CHECK(streamWaitValue64() != nullptr, SSAM_ERR_CUDA, "cuStreamWaitValue64 is not available");
+    CHECK(ctx->nRanks <= 32, SSAM_ERR_INVALID, "at most 32 ranks in an in-process group");
+    TRY(p2pAllocOwn(ctx));
+    for (int p = 0; p < ctx->nProcPatches; ++p) {
+        const int q = ctx->patchNbrRank[size_t(ctx->haloPatch[size_t(p)])];
+        CHECK(q >= 0 && q < int(ctx->localPeers.size()) && ctx->localPeers[size_t(q)] != ctx, SSAM_ERR_COMM,
+              "processor patch refers to a rank outside the in-process group");
+        ssam_ctx* nb = ctx->localPeers[size_t(q)];
+        CHECK(nb->haveMesh, SSAM_ERR_COMM, "in-process group: the neighbour rank has no mesh yet");
+        int pq = -1;
+        for (int k = 0; k < nb->nProcPatches; ++k)
+            if (nb->patchNbrRank[size_t(nb->haloPatch[size_t(k)])] == ctx->rank) pq = k;
+        CHECK(pq >= 0 && nb->haloOffsets[size_t(pq) + 1] - nb->haloOffsets[size_t(pq)] ==
+                             ctx->haloOffsets[size_t(p) + 1] - ctx->haloOffsets[size_t(p)],
+              SSAM_ERR_COMM, "processor patches of the two ranks do not match");
+        {
+            ssam_ctx* c2 = nb;  // allocate the neighbour's buffer if it has not reached its own set-up yet
+            ssam_status st = p2pAllocOwn(c2);
+            if (st != SSAM_OK) return fail(ctx, st, c2->err);
+        }
+        if (nb->device != ctx->device) {
+            CU(cudaSetDevice(ctx->device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(ctx, SSAM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        P.peerBase[p] = nb->p2p.recvBuf;
+        P.peerOff[p] = nb->haloOffsets[size_t(pq)];
+    }
+    CU(cudaSetDevice(ctx->device));
+    P.state = 1;
+    return SSAM_OK;
+}
+// sum of `n` doubles over the ranks of an in-process group, in rank order (host side; tiny and rare)
+ssam_status localAllReduce(ssam_ctx* ctx, double* dev, int n, int op /* 0 sum, 1 min, 2 max */,
+                           double* (*where)(ssam_ctx*)) {
+    std::vector<double> acc(size_t(n), 0.0), tmp(static_cast<size_t>(n));
+    for (size_t r = 0; r < ctx->localPeers.size(); ++r) {
+        ssam_ctx* q = ctx->localPeers[r];
+        CU(cudaSetDevice(q->device));
+        CU(cudaStreamSynchronize(q->stream));
+        CU(cudaMemcpy(tmp.data(), where(q), size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n; ++k)
+            acc[size_t(k)] = r == 0 ? tmp[size_t(k)]
+                                    : (op == 0 ? acc[size_t(k)] + tmp[size_t(k)]
+                                               : (op == 1 ? std::min(acc[size_t(k)], tmp[size_t(k)]) : std::max(acc[size_t(k)], tmp[size_t(k)])));
+    }
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dev, acc.data(), size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SSAM_OK;
+}
+
 ssam_status ensureHaloTransport(ssam_ctx* ctx) {
     if (ctx->nProcPatches == 0 || ctx->p2p.state != 0) return SSAM_OK;
+    if (!ctx->localPeers.empty()) return p2pSetupLocal(ctx);
     CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
     // every rank reaches its first exchange in the same call
     CU(cudaStreamSynchronize(ctx->stream));
@@ -703,7 +787,11 @@ ssam_status planesOf(ssam_ctx* ctx, const int* fields, int nFields, PlanePtrs& p
 
 ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cudaStream_t stream) {
     if (ctx->nProcPatches == 0 || nFields == 0) return SSAM_OK;
-    CHECK(ctx->comm != nullptr, SSAM_ERR_COMM, "mesh has processor patches but ssam_comm_init was not called");
+    CHECK(ctx->comm != nullptr || !ctx->localPeers.empty(), SSAM_ERR_COMM,
+          "mesh has processor patches but ssam_comm_init was not called");
+    CHECK(ctx->localPeers.empty() || !ctx->blocking, SSAM_ERR_INVALID,
+          "in-process rank group: collective calls need ssam_set_blocking(ctx, 0) on every rank (enqueue all ranks, "
+          "then synchronise)");
     TRY(ensureHaloTransport(ctx));
     PlanePtrs pl;
     int nc = 0;
@@ -749,7 +837,25 @@ ssam_status ensureFricSums(ssam_ctx* ctx, int patch) {
     const int b0 = ctx->patchStart[patch] - ctx->nIF;
     LAUNCH(k_patch_sums, 1, 32, b0, ctx->patchSize[patch], ctx->Cpl[0], ctx->Cpl[1], ctx->Cpl[2], ctx->magSf_b,
            ctx->nCells, ctx->fricSums);
-    if (ctx->comm && ctx->nRanks > 1) {
+    if (!ctx->localPeers.empty() && ctx->nRanks > 1) {
+        // in-process group: every rank's local sums (computed here for the ranks that have not needed them yet)
+        for (ssam_ctx* q : ctx->localPeers) {
+            if (q == ctx || q->fricLocalFor == patch) continue;
+            CHECK(q->haveMesh && patch < q->nPatches, SSAM_ERR_COMM, "in-process group: neighbour rank has no such patch");
+            CU(cudaSetDevice(q->device));
+            if (!q->fricSums) {
+                ssam_status st = devAlloc(q, &q->fricSums, 8);
+                if (st != SSAM_OK) return fail(ctx, st, q->err);
+            }
+            k_patch_sums<<<1, 32, 0, q->stream>>>(q->patchStart[size_t(patch)] - q->nIF, q->patchSize[size_t(patch)], q->Cpl[0],
+                                                  q->Cpl[1], q->Cpl[2], q->magSf_b, q->nCells, q->fricSums);
+            q->launches++;
+            q->fricLocalFor = patch;
+        }
+        CU(cudaSetDevice(ctx->device));
+        ctx->fricLocalFor = patch;
+        TRY(localAllReduce(ctx, ctx->fricSums + 4, 4, 0, [](ssam_ctx* q) { return q->fricSums; }));
+    } else if (ctx->comm && ctx->nRanks > 1) {
         // reduce(patchCenter_, sumOp<vector>()); reduce(patchArea_, sumOp<scalar>())  (constantSlipStick.C:134-135)
         // NB every rank starts its area at VSMALL like the reference does.
         NC(nccl().AllReduce(ctx->fricSums, ctx->fricSums + 4, 4, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
@@ -934,7 +1040,7 @@ ssam_status gradOrStrain(ssam_ctx* ctx, bool strain, double factor, int outField
     UpdateArgs a;
     fillMeshArgs(ctx, a);
     a.pfDist = ctx->pfDist;
-    a.pfDistU = a.pfDist + ctx->bandwidthTiles;
+    a.pfDistU = a.pfDist + ctx->pfBandwidthTiles;
     const bool tiled = ctx->cellKernel >= 1;
     if (strain) {
         TRY(ensureField(ctx, outField));
@@ -1005,7 +1111,7 @@ int mapGrid(const ssam_ctx* c) { return std::min(gridFor(c->nTot, 256), 148 * 32
 // renumbered, so the per-cell summation order - and with it every result bit - is unchanged.
 ssam_status buildTileOrder(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     devFree(ctx->tileOrder);
-    const long long reuseBytes = (long long)ctx->bandwidthTiles * TILE * 270;
+    const long long reuseBytes = (long long)ctx->pfBandwidthTiles * TILE * 270;  // reuse distance of the heavy gathers
     if (reuseBytes < (40ll << 20) || ctx->nTiles < 4) return SSAM_OK;  // natural order already fits L2
     static const int bfs = std::getenv("SSAM_BFS_ORDER") ? std::atoi(std::getenv("SSAM_BFS_ORDER")) : 1;
     if (!bfs) return SSAM_OK;
@@ -1059,11 +1165,17 @@ struct PermutedMesh {
     std::vector<double> Sf, w, V, C;
 };
 
-// SSAM_TILE_ORDER=0: tiles in seed (caller) order; 1 (default): Morton order of the tile centroids within 16 coarse
-// caller-order buckets
+// Order of the tiles of the tile-compact layout in memory (= the order the cell kernel walks them).  SSAM_TILE_ORDER:
+//   -1 (default) automatic: seed order, unless the heavy out-of-tile gathers would then be further away than L2
+//      holds (planes wider than ~256 x 512 cells), in which case the pencil order;
+//    0 seed order (tiles in the order of their first run in the caller's numbering);
+//    1 Morton order of the tile centroids within 16 coarse caller-order buckets (measured: never the best);
+//    2 pencil order (long tile direction slowest).
+// Measured on one B200 (profiles/r2_tile_order.md): 256x256 planes seed 0.78-0.80 / pencil 0.75-0.77 of HBM; 512-wide
+// planes seed 0.68 / pencil 0.73.
 int tileOrderModeFromEnv() {
     const char* e = std::getenv("SSAM_TILE_ORDER");
-    return e ? std::atoi(e) : 1;
+    return e ? std::atoi(e) : -1;
 }
 
 // -> perm (library position -> caller cell); returns false when clustering does not pay
@@ -1143,6 +1255,24 @@ bool computeCompactOrder(int layoutMode, int tileOrderMode, const ssam_mesh_desc
     // (512x512 planes: 140 MB of traffic, more than the 126 MB L2 keeps -> the out-of-tile gathers miss).  A Morton
     // (Z-order) curve over the tile centroids bounds the reuse distance by the surface of a sub-cube instead.
     // Integer/geometry preprocessing only: per-cell face order, and with it every result bit, is unchanged.
+    if (tileOrderMode < 0) {
+        // automatic: 97th percentile of the tile distance of the internal faces in seed order = how far back the heavy
+        // gathers reach; beyond ~48 MB of per-tile traffic (64 KB per tile) they miss L2
+        std::vector<int> tileOfRun(size_t(nB), 0);
+        for (size_t i = 0; i < full.size(); ++i) tileOfRun[size_t(full[i])] = int(i / RUNS_PER_TILE);
+        const int nFull = int(full.size() / RUNS_PER_TILE);
+        for (size_t i = 0; i < partial.size(); ++i) tileOfRun[size_t(partial[i])] = nFull + int(i / RUNS_PER_TILE);
+        std::vector<int> dist;
+        dist.reserve(size_t(nIF) / 16 + 1);
+        for (int f = 0; f < nIF; f += 16)
+            dist.push_back(std::abs(tileOfRun[size_t(m->neighbour[f] / RUN)] - tileOfRun[size_t(m->owner[f] / RUN)]));
+        tileOrderMode = 0;
+        if (!dist.empty()) {
+            const size_t k = std::min(dist.size() - 1, size_t(0.97 * double(dist.size())));
+            std::nth_element(dist.begin(), dist.begin() + long(k), dist.end());
+            if ((long long)dist[k] * 65536ll > (48ll << 20)) tileOrderMode = 2;
+        }
+    }
     if (tileOrderMode == 1 && full.size() >= size_t(8 * RUNS_PER_TILE)) {
         const size_t nT = full.size() / RUNS_PER_TILE;
         std::vector<double> cen(nT * 3, 0.0);
@@ -1188,6 +1318,81 @@ bool computeCompactOrder(int layoutMode, int tileOrderMode, const ssam_mesh_desc
         ordered.reserve(full.size());
         for (const auto& kt : key)
             for (int r = 0; r < RUNS_PER_TILE; ++r) ordered.push_back(full[size_t(kt.second) * RUNS_PER_TILE + size_t(r)]);
+        full.swap(ordered);
+    }
+    // tileOrderMode 2: "pencil" order.  Tiles are elongated along the caller's fastest index (a 64 x 2 x 2 brick shares
+    // 128 faces with each of its four y/z neighbours but only 4 with an x neighbour), so the heavy out-of-tile gathers
+    // are the ones across the tile's two SHORT directions.  Sorting the tiles lexicographically with the long
+    // direction slowest puts those neighbours 1 tile and one pencil (nz/2 tiles, a few MB) away instead of one whole
+    // layer of bricks (512x512 planes: 134 MB > L2); only the light x gathers (3 % of the cells) become far.
+    if (tileOrderMode == 2 && full.size() >= size_t(8 * RUNS_PER_TILE)) {
+        const size_t nT = full.size() / RUNS_PER_TILE;
+        std::vector<double> cen(nT * 3, 0.0);
+        double ext[3] = {0.0, 0.0, 0.0};
+        for (size_t t = 0; t < nT; ++t) {
+            double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+            for (int r = 0; r < RUNS_PER_TILE; ++r) {
+                const int b = full[t * RUNS_PER_TILE + size_t(r)];
+                const int c0 = b * RUN, c1 = std::min(nC, (b + 1) * RUN) - 1;
+                for (int k = 0; k < 3; ++k) {
+                    const double x0 = m->C[size_t(c0) * 3 + size_t(k)], x1 = m->C[size_t(c1) * 3 + size_t(k)];
+                    cen[t * 3 + size_t(k)] += 0.5 * (x0 + x1) / RUNS_PER_TILE;
+                    lo[k] = std::min({lo[k], x0, x1});
+                    hi[k] = std::max({hi[k], x0, x1});
+                }
+            }
+            for (int k = 0; k < 3; ++k) ext[k] += (hi[k] - lo[k]) / double(nT);
+        }
+        // levels along an axis: clusters of (nearly) equal centroid coordinates
+        std::vector<int> level[3];
+        int nLevels[3];
+        for (int k = 0; k < 3; ++k) {
+            std::vector<std::pair<double, int>> v(nT);
+            for (size_t t = 0; t < nT; ++t) v[t] = {cen[t * 3 + size_t(k)], int(t)};
+            std::sort(v.begin(), v.end());
+            const double tol = 0.25 * std::max(ext[k], (v.back().first - v.front().first) / double(nT));
+            level[k].assign(nT, 0);
+            int lv = 0;
+            double start = v[0].first;
+            for (size_t i = 0; i < nT; ++i) {
+                if (v[i].first - start > tol) {
+                    ++lv;
+                    start = v[i].first;
+                }
+                level[k][size_t(v[i].second)] = lv;
+            }
+            nLevels[k] = lv + 1;
+        }
+        // slowest axis = the direction across which the tiles share the FEWEST faces (the tiles' long direction),
+        // judged from the face normals of the inter-tile faces, not from cell shapes
+        long long crossing[3] = {0, 0, 0};
+        {
+            std::vector<int> tileOfRun2(size_t(nB), -1);
+            for (size_t i = 0; i < full.size(); ++i) tileOfRun2[size_t(full[i])] = int(i / RUNS_PER_TILE);
+            for (int f = 0; f < nIF; f += 7) {
+                const int ta = tileOfRun2[size_t(m->owner[f] / RUN)], tb = tileOfRun2[size_t(m->neighbour[f] / RUN)];
+                if (ta == tb) continue;
+                const double sx = std::fabs(m->Sf[size_t(f) * 3]), sy = std::fabs(m->Sf[size_t(f) * 3 + 1]),
+                             sz = std::fabs(m->Sf[size_t(f) * 3 + 2]);
+                ++crossing[sx >= sy && sx >= sz ? 0 : (sy >= sz ? 1 : 2)];
+            }
+        }
+        int A = 0;
+        for (int k = 1; k < 3; ++k)
+            if (crossing[k] < crossing[A]) A = k;
+        int B = (A + 1) % 3, Cx = (A + 2) % 3;
+        if (nLevels[Cx] > nLevels[B]) std::swap(B, Cx);  // fastest: the short direction with the fewest levels
+        std::vector<int> idx(nT);
+        for (size_t t = 0; t < nT; ++t) idx[t] = int(t);
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+            if (level[A][size_t(x)] != level[A][size_t(y)]) return level[A][size_t(x)] < level[A][size_t(y)];
+            if (level[B][size_t(x)] != level[B][size_t(y)]) return level[B][size_t(x)] < level[B][size_t(y)];
+            return level[Cx][size_t(x)] < level[Cx][size_t(y)];
+        });
+        std::vector<int> ordered;
+        ordered.reserve(full.size());
+        for (int t : idx)
+            for (int r = 0; r < RUNS_PER_TILE; ++r) ordered.push_back(full[size_t(t) * RUNS_PER_TILE + size_t(r)]);
         full.swap(ordered);
     }
     perm.clear();
@@ -1280,6 +1485,7 @@ ssam_status ssam_create(ssam_ctx** out, int device) {
 }
 
 ssam_status ssam_destroy(ssam_ctx* ctx) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     if (!ctx) return SSAM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -1300,12 +1506,14 @@ ssam_status ssam_destroy(ssam_ctx* ctx) {
 const char* ssam_last_error(const ssam_ctx* ctx) { return ctx ? ctx->err.c_str() : g_globalErr.c_str(); }
 
 ssam_status ssam_sync(ssam_ctx* ctx) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
 }
 
 ssam_status ssam_set_stream(ssam_ctx* ctx, void* s) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->stream = s ? reinterpret_cast<cudaStream_t>(s) : ctx->ownStream;
@@ -1313,6 +1521,7 @@ ssam_status ssam_set_stream(ssam_ctx* ctx, void* s) {
 }
 
 ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     ctx->blocking = blocking != 0;
     return SSAM_OK;
@@ -1321,12 +1530,14 @@ ssam_status ssam_set_blocking(ssam_ctx* ctx, int blocking) {
 int64_t ssam_launch_count(const ssam_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 ssam_status ssam_set_host_chunks(ssam_ctx* ctx, int n) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     ctx->hostChunks = n;
     return SSAM_OK;
 }
 
 ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CHECK(variant >= 0 && variant <= 2, SSAM_ERR_INVALID,
           "cell kernel variant must be 0 (direct), 1 (tiled, one CTA per tile) or 2 (persistent, self-pipelined)");
@@ -1335,6 +1546,7 @@ ssam_status ssam_set_cell_kernel(ssam_ctx* ctx, int variant) {
 }
 
 ssam_status ssam_set_cell_layout(ssam_ctx* ctx, int mode) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CHECK(mode >= SSAM_LAYOUT_CALLER && mode <= SSAM_LAYOUT_COMPACT, SSAM_ERR_INVALID, "bad cell layout mode");
     ctx->layoutMode = mode;
@@ -1361,12 +1573,14 @@ ssam_status ssam_compact_cell_order(const ssam_mesh_desc* m, int32_t* order, dou
 }
 
 ssam_status ssam_profile_enable(ssam_ctx* ctx, int enable) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     ctx->profile = enable != 0;
     return SSAM_OK;
 }
 
 ssam_status ssam_profile_get(ssam_ctx* ctx, double* ms, int64_t* n) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && ms && n, SSAM_ERR_INVALID, "null argument");
     CU(cudaStreamSynchronize(ctx->stream));
     double total = 0.0;
@@ -1385,7 +1599,7 @@ ssam_status ssam_profile_get(ssam_ctx* ctx, double* ms, int64_t* n) {
 }
 
 // ---- mesh -------------------------------------------------------------------------------------------
-ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
+static ssam_status meshSetImpl(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     CHECK(ctx && m, SSAM_ERR_INVALID, "null argument");
     CU(cudaSetDevice(ctx->device));
     CHECK(m->nCells > 0 && m->nInternalFaces >= 0 && m->nFaces >= m->nInternalFaces && m->nPatches >= 0,
@@ -1400,14 +1614,24 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     ssam_mesh_desc mm;
     const ssam_mesh_desc* callerMesh = m;
     bool permuted = false;
-    if (ctx->layoutMode != SSAM_LAYOUT_CALLER && m->nCells >= 2 * TILE && m->nInternalFaces > 0 && m->neighbour) {
-        for (int f = 1; f < m->nInternalFaces; ++f)
-            CHECK(m->owner[f] >= m->owner[f - 1], SSAM_ERR_INVALID,
-                  "owner[] of the internal faces is not ascending: the mesh is not in upper-triangular order");
-        for (int f = 0; f < m->nFaces; ++f)
-            CHECK(m->owner[f] >= 0 && m->owner[f] < m->nCells &&
-                      (f >= m->nInternalFaces || (m->neighbour[f] >= 0 && m->neighbour[f] < m->nCells)),
-                  SSAM_ERR_INVALID, "owner / neighbour label out of range");
+    CHECK(m->nInternalFaces == 0 || m->neighbour, SSAM_ERR_INVALID, "null neighbour array");
+    for (int f = 1; f < m->nInternalFaces; ++f)
+        CHECK(m->owner[f] >= m->owner[f - 1], SSAM_ERR_INVALID,
+              "owner[] of the internal faces is not ascending: the mesh is not in upper-triangular order");
+    for (int f = 0; f < m->nFaces; ++f)
+        CHECK(m->owner[f] >= 0 && m->owner[f] < m->nCells &&
+                  (f >= m->nInternalFaces || (m->neighbour[f] >= 0 && m->neighbour[f] < m->nCells)),
+              SSAM_ERR_INVALID, "owner / neighbour label out of range");
+    for (int p = 0; p < m->nPatches; ++p) {
+        CHECK(m->patchKind[p] == SSAM_PATCH_GENERIC || m->patchKind[p] == SSAM_PATCH_PROCESSOR ||
+                  (m->patchKind[p] == SSAM_PATCH_EMPTY && m->patchSize[p] == 0),
+              SSAM_ERR_INVALID,
+              "unsupported patch kind: empty patches with faces (2-D / 1-D cases) carry zero-size fields in OpenFOAM and "
+              "are not part of this 3-D path");
+        CHECK(m->patchKind[p] != SSAM_PATCH_PROCESSOR || m->patchNbrRank[p] >= 0, SSAM_ERR_INVALID,
+              "processor patch without a neighbour rank");
+    }
+    if (ctx->layoutMode != SSAM_LAYOUT_CALLER && m->nCells >= 2 * TILE && m->nInternalFaces > 0) {
         if (computeCompactOrder(ctx->layoutMode, tileOrderModeFromEnv(), m, pm.perm, ctx->remotePerCellCaller,
                                 ctx->remotePerCellCompact)) {
             permuteMesh(m, pm);
@@ -1441,7 +1665,6 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
         expect += ctx->patchSize[p];
     }
     CHECK(expect == ctx->nFaces, SSAM_ERR_INVALID, "patches do not cover the boundary faces");
-    ctx->haveMesh = true;
 
     const size_t nF = size_t(ctx->nFaces), nC = size_t(ctx->nCells), nB = size_t(ctx->nBnd);
     TRY(devAlloc(ctx, &ctx->owner, nF));
@@ -1512,6 +1735,17 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
                            cudaMemcpyHostToDevice, ctx->stream));
     }
     TRY(buildAddressing(ctx));
+    {
+        std::vector<int> dist;
+        dist.reserve(size_t(ctx->nIF) / 8 + 1);
+        for (int f = 0; f < ctx->nIF; f += 8) dist.push_back(std::abs(m->neighbour[f] / TILE - m->owner[f] / TILE));
+        ctx->pfBandwidthTiles = ctx->bandwidthTiles;
+        if (!dist.empty()) {
+            const size_t k = std::min(dist.size() - 1, size_t(0.97 * double(dist.size())));
+            std::nth_element(dist.begin(), dist.begin() + long(k), dist.end());
+            ctx->pfBandwidthTiles = std::min(ctx->bandwidthTiles, dist[k] + 1);
+        }
+    }
     if (ctx->nProcPatches == 0) TRY(buildTileOrder(ctx, m));
     if (permuted) {
         // from here on uploads / downloads of cell values go through the permutation
@@ -1526,7 +1760,26 @@ ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     return SSAM_OK;
 }
 
+// the mesh becomes usable only when the whole build succeeded; a failed build leaves no half-built mesh behind
+ssam_status ssam_mesh_set(ssam_ctx* ctx, const ssam_mesh_desc* m) {
+    if (ctx) cudaSetDevice(ctx->device);
+    const ssam_status st = meshSetImpl(ctx, m);
+    if (ctx) {
+        if (st == SSAM_OK) {
+            ctx->haveMesh = true;
+        } else {
+            const std::string e = ctx->err;
+            cudaStreamSynchronize(ctx->stream);
+            cudaGetLastError();
+            freeMesh(ctx);
+            ctx->err = e;
+        }
+    }
+    return st;
+}
+
 ssam_status ssam_patch_u_bc_set(ssam_ctx* ctx, const int32_t* kinds) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && ctx->haveMesh && kinds, SSAM_ERR_INVALID, "mesh not set / null kinds");
     for (int p = 0; p < ctx->nPatches; ++p) {
         CHECK(kinds[p] == SSAM_BC_VALUE || kinds[p] == SSAM_BC_ZERO_GRADIENT, SSAM_ERR_INVALID, "bad U bc kind");
@@ -1626,6 +1879,7 @@ static ssam_status ensureRefAddr(ssam_ctx* ctx) {
 }
 
 ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && ctx->haveMesh && n, SSAM_ERR_INVALID, "mesh not set");
     if (which == SSAM_ADDR_CELL_ORDER) {
         *n = ctx->nCells;
@@ -1652,6 +1906,7 @@ ssam_status ssam_addressing_size(ssam_ctx* ctx, int which, int64_t* n) {
 }
 
 ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t n) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     int64_t have = 0;
     TRY(ssam_addressing_size(ctx, which, &have));
     CHECK(out && n == have, SSAM_ERR_INVALID, "size mismatch");
@@ -1714,6 +1969,7 @@ ssam_status ssam_addressing_get(ssam_ctx* ctx, int which, int32_t* out, int64_t 
 
 // ---- fields -------------------------------------------------------------------------------------------
 ssam_status ssam_field_upload(ssam_ctx* ctx, int field, const double* internal, const double* boundary) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     TRY(ensureField(ctx, field));
     const int nc = ncompOf(field);
@@ -1729,6 +1985,7 @@ ssam_status ssam_field_upload(ssam_ctx* ctx, int field, const double* internal, 
 }
 
 ssam_status ssam_field_download(ssam_ctx* ctx, int field, double* internal, double* boundary) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CHECK(field >= 0 && field < SSAM_F_COUNT, SSAM_ERR_INVALID, "bad field id");
     TRY(need(ctx, field, "download of a field that was never uploaded or computed"));
@@ -1740,6 +1997,7 @@ ssam_status ssam_field_download(ssam_ctx* ctx, int field, double* internal, doub
 }
 
 ssam_status ssam_field_device_ptr(ssam_ctx* ctx, int field, int comp, void** ptr, int64_t* len) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && ptr, SSAM_ERR_INVALID, "null argument");
     TRY(ensureField(ctx, field));
     CHECK(comp >= 0 && comp < ncompOf(field), SSAM_ERR_INVALID, "bad component");
@@ -1757,6 +2015,7 @@ int ssam_field_is_set(const ssam_ctx* ctx, int field) {
 
 // ---- boundary condition ---------------------------------------------------------------------------------
 ssam_status ssam_bc_rotational_slip(ssam_ctx* ctx, const ssam_rotslip_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set / null params");
     CHECK(p->patch >= 0 && p->patch < ctx->nPatches, SSAM_ERR_INVALID, "patch out of range");
     CHECK(p->model == SSAM_ROTSLIP_CONSTANT || p->model == SSAM_ROTSLIP_EXPONENTIAL, SSAM_ERR_UNKNOWN_MODEL,
@@ -1770,12 +2029,14 @@ ssam_status ssam_bc_rotational_slip(ssam_ctx* ctx, const ssam_rotslip_params* p)
 
 // ---- staged entry points ----------------------------------------------------------------------------------
 ssam_status ssam_grad_u(ssam_ctx* ctx) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     TRY(gradOrStrain(ctx, false, 0.0, SSAM_F_GRADU));
     return finish(ctx);
 }
 
 ssam_status ssam_strain_rate(ssam_ctx* ctx, double factor, int out_field) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CHECK(out_field == SSAM_F_EPSDOT || out_field == SSAM_F_STRAINRATE, SSAM_ERR_INVALID,
           "strain rate goes to EPSDOT or STRAINRATE");
@@ -1784,12 +2045,14 @@ ssam_status ssam_strain_rate(ssam_ctx* ctx, double factor, int out_field) {
 }
 
 ssam_status ssam_viscosity_correct(ssam_ctx* ctx, int phase, const ssam_viscosity_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     TRY(viscosityCorrect(ctx, phase, p));
     return finish(ctx);
 }
 
 ssam_status ssam_mixture_calc_nu(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     TRY(mixtureCalcNu(ctx, p));
     return finish(ctx);
@@ -1797,6 +2060,7 @@ ssam_status ssam_mixture_calc_nu(ssam_ctx* ctx, const ssam_mixture_params* p) {
 
 ssam_status ssam_thermo_correct(ssam_ctx* ctx, const ssam_viscosity_params* v1, const ssam_viscosity_params* v2,
                                 const ssam_mixture_params* mix) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && mix, SSAM_ERR_INVALID, "null argument");
     TRY(viscosityCorrect(ctx, 1, v1));  // nuModel1_->correct()   (...Mixture.C:43)
     TRY(viscosityCorrect(ctx, 2, v2));  // nuModel2_->correct()   (:44)
@@ -1805,6 +2069,7 @@ ssam_status ssam_thermo_correct(ssam_ctx* ctx, const ssam_viscosity_params* v1, 
 }
 
 ssam_status ssam_mixture_mu(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(need(ctx, SSAM_F_NU1, "nu1"));
@@ -1827,16 +2092,19 @@ static ssam_status mixtureLinear(ssam_ctx* ctx, int outField, double v1, double 
 }
 
 ssam_status ssam_mixture_rho(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     return mixtureLinear(ctx, SSAM_F_RHO, p->rho1, p->rho2);
 }
 
 ssam_status ssam_mixture_cp(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     return mixtureLinear(ctx, SSAM_F_CP, p->cp1, p->cp2);
 }
 
 ssam_status ssam_mixture_k(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(need(ctx, SSAM_F_T, "temp"));
@@ -1851,6 +2119,7 @@ ssam_status ssam_mixture_k(ssam_ctx* ctx, const ssam_mixture_params* p) {
 }
 
 ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(ensureField(ctx, SSAM_F_RHO_SOLVER));
@@ -1862,6 +2131,7 @@ ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p) {
 }
 
 ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     TRY(need(ctx, SSAM_F_EPSDOT, "epsilonDotEq"));
     TRY(need(ctx, SSAM_F_T, "temp"));
@@ -1893,6 +2163,7 @@ ssam_status ssam_stress_strain(ssam_ctx* ctx, const ssam_stress_strain_params* p
 
 // explicit part of turbulence.divDevRhoReff(rho, U)  (fluid/UEqn.H:13)
 ssam_status ssam_div_dev_rho_reff_explicit(ssam_ctx* ctx) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     TRY(need(ctx, SSAM_F_GRADU, "gradU (ssam_grad_u, or ssam_update_fused with flag 1)"));
     TRY(need(ctx, SSAM_F_RHO_SOLVER, "rho (ssam_solver_rho_rhocp)"));
@@ -1924,6 +2195,7 @@ ssam_status ssam_div_dev_rho_reff_explicit(ssam_ctx* ctx) {
 
 // interfaceProperties::correct() -> calculateK()  (immiscibleIncompressibleTwoPhaseThermalMixture.H:80)
 ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     TRY(need(ctx, SSAM_F_ALPHA1, "alpha1"));
     TRY(ensureField(ctx, SSAM_F_GRADALPHA));
@@ -1955,7 +2227,7 @@ ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags)
     a.tileDesc = ctx->tileDesc;
     a.tileCount = ctx->nTiles;
     a.pfDist = ctx->pfDist;
-    a.pfDistU = a.pfDist + ctx->bandwidthTiles;
+    a.pfDistU = a.pfDist + ctx->pfBandwidthTiles;
     const int smem = int(sizeof(TileSmem));
     if (tiled) {
         static bool configured[64] = {false};
@@ -1987,6 +2259,7 @@ ssam_status ssam_interface_correct(ssam_ctx* ctx, double deltaN, unsigned flags)
 }
 
 ssam_status ssam_face_field_download(ssam_ctx* ctx, int ff, double* internal_faces, double* boundary_faces) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CHECK(ff >= 0 && ff < SSAM_FF_COUNT, SSAM_ERR_INVALID, "bad face field id");
     CHECK(ctx->faceField[ff] && ctx->faceFieldSet[ff], SSAM_ERR_MISSING_FIELD,
@@ -2042,6 +2315,7 @@ static ssam_status mixtureFaceVisc(ssam_ctx* ctx, const ssam_mixture_params* p, 
     return finish(ctx);
 }
 ssam_status ssam_face_interpolate(ssam_ctx* ctx, int field, int ff) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx, SSAM_ERR_INVALID, "null context");
     CHECK(field >= 0 && field < SSAM_F_COUNT && ncompOf(field) == 1, SSAM_ERR_INVALID, "scalar field id expected");
     CHECK(ff >= 0 && ff < SSAM_FF_COUNT, SSAM_ERR_INVALID, "bad face field id");
@@ -2066,6 +2340,7 @@ ssam_status ssam_mixture_muf(ssam_ctx* ctx, const ssam_mixture_params* p) { retu
 ssam_status ssam_mixture_nuf(ssam_ctx* ctx, const ssam_mixture_params* p) { return mixtureFaceVisc(ctx, p, true); }
 
 ssam_status ssam_field_min_max(ssam_ctx* ctx, int field, double* min_value, double* max_value) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && min_value && max_value, SSAM_ERR_INVALID, "null argument");
     CHECK(field >= 0 && field < SSAM_F_COUNT && ncompOf(field) == 1, SSAM_ERR_INVALID, "scalar field id expected");
     TRY(need(ctx, field, "min/max of a field that was never set"));
@@ -2074,7 +2349,10 @@ ssam_status ssam_field_min_max(ssam_ctx* ctx, int field, double* min_value, doub
     double* out = ctx->minmaxScratch + 2 * 148 * 8;
     LAUNCH(k_minmax, nBlocks, 256, ctx->plane[field][0], ctx->nTot, ctx->minmaxScratch);
     LAUNCH(k_minmax_final, 1, 256, ctx->minmaxScratch, nBlocks, out);
-    if (ctx->comm && ctx->nRanks > 1) {
+    if (!ctx->localPeers.empty() && ctx->nRanks > 1) {
+        return fail(ctx, SSAM_ERR_COMM, "ssam_field_min_max across an in-process rank group: reduce the per-rank values "
+                                        "on the host");
+    } else if (ctx->comm && ctx->nRanks > 1) {
         NcclApi& N = nccl();
         NC(N.GroupStart());
         NC(N.AllReduce(out, out, 1, ncclFloat64, ncclMin, ctx->comm, ctx->stream));
@@ -2091,11 +2369,13 @@ ssam_status ssam_field_min_max(ssam_ctx* ctx, int field, double* min_value, doub
 }
 
 ssam_status ssam_interface_nhatf_download(ssam_ctx* ctx, double* internal_faces, double* boundary_faces) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     return ssam_face_field_download(ctx, SSAM_FF_NHATF, internal_faces, boundary_faces);
 }
 double* ssam_interface_nhatf_device_ptr(ssam_ctx* ctx) { return ssam_face_field_device_ptr(ctx, SSAM_FF_NHATF); }
 
 ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && deltaN, SSAM_ERR_INVALID, "null argument");
     CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
     double sn[2] = {ctx->sumV, double(ctx->nCells)};
@@ -2114,6 +2394,7 @@ ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN) {
 }
 
 ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
     CHECK(p->model == SSAM_STICK_CONSTANT || p->model == SSAM_STICK_EXPONENTIAL, SSAM_ERR_UNKNOWN_MODEL,
           "Unknown stickModel type");
@@ -2128,6 +2409,7 @@ ssam_status ssam_friction_correct(ssam_ctx* ctx, const ssam_stick_params* p) {
 }
 
 ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* area) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && centre && area, SSAM_ERR_INVALID, "null argument");
     CHECK(ctx->fricPatchCached >= 0, SSAM_ERR_INVALID, "no friction patch evaluated yet");
     double s[4];
@@ -2197,7 +2479,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     a.d1 = deriveVisc(p->visc1);
     a.pfDist = ctx->pfDist;
     if (const char* pf = std::getenv("SSAM_PF")) a.pfDist = std::atoi(pf);
-    a.pfDistU = a.pfDist + ctx->bandwidthTiles;
+    a.pfDistU = a.pfDist + ctx->pfBandwidthTiles;
 
     // nu2 (Newtonian, constant): written only when the value changes or something else wrote the plane
     if (!ctx->nu2Filled || ctx->nu2FilledWith != p->visc2.nu) {
@@ -2219,6 +2501,9 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     //      on a high-priority second stream beside the interior tiles.
     const bool haloInputs = ctx->nProcPatches && (flags & 2);
     const bool split = ctx->nProcPatches > 0 && ctx->cellKernel >= 1;
+    CHECK(ctx->nProcPatches == 0 || ctx->localPeers.empty() || !ctx->blocking, SSAM_ERR_INVALID,
+          "in-process rank group: collective calls need ssam_set_blocking(ctx, 0) on every rank (enqueue all ranks, "
+          "then synchronise)");
     if (ctx->nProcPatches) TRY(ensureHaloTransport(ctx));
     const bool peer = split && ctx->p2p.state == 1;
     if (split && !peer && !ctx->commStream) {
@@ -2318,6 +2603,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
 }
 
 ssam_status ssam_update_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     TRY(updateFusedAsync(ctx, p, flags));
     return finish(ctx);
 }
@@ -2533,6 +2819,7 @@ static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_par
 }
 
 ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, const ssam_host_io* io) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p && io, SSAM_ERR_INVALID, "null argument");
     CHECK(ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
     CHECK(io->U_i && io->T_i && io->alpha1_i, SSAM_ERR_INVALID, "U, temp and alpha1 host buffers are required");
@@ -2550,6 +2837,7 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
 
 // ---- device-math evaluation (tests) -----------------------------------------------------------------------------
 ssam_status ssam_debug_math(ssam_ctx* ctx, int fn, const double* x, const double* y, double* out, int64_t n) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && x && out && n >= 0, SSAM_ERR_INVALID, "null argument");
     if (n == 0) return SSAM_OK;
     double *dx = nullptr, *dy = nullptr, *dout = nullptr;
@@ -2571,6 +2859,7 @@ ssam_status ssam_debug_math(ssam_ctx* ctx, int fn, const double* x, const double
 
 // ---- FP64 issue ceiling ------------------------------------------------------------------------------------------------
 ssam_status ssam_measure_fp64_peak(ssam_ctx* ctx, double* fp64_instr_per_s) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && fp64_instr_per_s, SSAM_ERR_INVALID, "null argument");
     CU(cudaSetDevice(ctx->device));
     int sms = 0;
@@ -2613,6 +2902,7 @@ ssam_status ssam_comm_unique_id(void* id_out) {
 }
 
 ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int nRanks) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && id, SSAM_ERR_INVALID, "null argument");
     CHECK(nRanks >= 1 && rank >= 0 && rank < nRanks, SSAM_ERR_INVALID, "bad rank / nRanks");
     if (!nccl().load()) return fail(ctx, SSAM_ERR_COMM, nccl().error);
@@ -2626,6 +2916,23 @@ ssam_status ssam_comm_init(ssam_ctx* ctx, const void* id, int rank, int nRanks) 
     return SSAM_OK;
 }
 
+ssam_status ssam_comm_init_local(ssam_ctx** ctxs, int nRanks) {
+    ssam_ctx* ctx = nullptr;
+    CHECK(ctxs && nRanks >= 1 && nRanks <= 32, SSAM_ERR_INVALID, "bad in-process rank group");
+    for (int r = 0; r < nRanks; ++r) CHECK(ctxs[r] != nullptr, SSAM_ERR_INVALID, "null context in the rank group");
+    for (int r = 0; r < nRanks; ++r) {
+        ssam_ctx* c = ctxs[r];
+        CHECK(c->comm == nullptr, SSAM_ERR_INVALID, "context already has an NCCL communicator");
+        c->localPeers.assign(ctxs, ctxs + nRanks);
+        c->rank = r;
+        c->nRanks = nRanks;
+        c->fricPatchCached = -1;
+        c->fricLocalFor = -1;
+        p2pFree(c);
+    }
+    return SSAM_OK;
+}
+
 int64_t ssam_halo_bytes_last_update(const ssam_ctx* ctx) { return ctx ? int64_t(ctx->haloBytesLastUpdate) : 0; }
 
 int ssam_halo_transport(const ssam_ctx* ctx) {
@@ -2634,6 +2941,7 @@ int ssam_halo_transport(const ssam_ctx* ctx) {
 }
 
 ssam_status ssam_halo_exchange(ssam_ctx* ctx, uint32_t mask) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
     for (int f = 0; f < SSAM_F_COUNT; ++f)
         if (mask & (1u << f)) {

@@ -90,4 +90,4 @@ def test_cfg3_polyhedral_mid_size(ctx):
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
         oc = oracle_update(case, O.FUSED, ctx=ctx)
         compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU])
-    ctx.set_cell_kernel(2)
+    ctx.set_cell_kernel(1)

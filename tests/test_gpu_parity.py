@@ -61,7 +61,7 @@ def test_fused_update_matches_oracle(ctx, name, variant):
     try:
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
     finally:
-        ctx.set_cell_kernel(2)
+        ctx.set_cell_kernel(1)
     oc = oracle_update(case, O.FAITHFUL, ctx=ctx)
     report = {}
     compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU, P.F_U], report)
@@ -78,7 +78,7 @@ def test_tiled_kernel_capacity_fallback(ctx):
         ctx.set_cell_kernel(variant)
         ctx.update_fused(case.params, capi.FUSED_WRITE_GRAD)
         res[variant] = {f: ctx.download(f) for f in case.outputs + [P.F_GRADU]}
-    ctx.set_cell_kernel(2)
+    ctx.set_cell_kernel(1)
     for f in res[0]:
         for v in (1, 2):
             assert np.array_equal(res[0][f][0], res[v][f][0], equal_nan=True), (v, P.FIELD_NAMES[f])
@@ -261,7 +261,7 @@ def test_degenerate_meshes(ctx, dims):
         compare_ctx_oracle(ctx, oc, case.outputs + [P.F_GRADU])
         for which in (P.ADDR_OWNER_START, P.ADDR_EXTRA_START, P.ADDR_EXTRA_FACE, P.ADDR_CELL_FACES, P.ADDR_FACE_COLOUR):
             assert ctx.addressing(which).tobytes() == oc.addressing(which).tobytes()
-    ctx.set_cell_kernel(2)
+    ctx.set_cell_kernel(1)
 
 
 @pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg3_poly"])
@@ -305,7 +305,7 @@ def test_interface_correct_matches_oracle(ctx, name, variant):
     try:
         ctx.interface_correct(dn)
     finally:
-        ctx.set_cell_kernel(2)
+        ctx.set_cell_kernel(1)
     oc.interface_correct(dn)
     for f in (P.F_GRADALPHA, P.F_CURVATURE):
         gi, gb = ctx.download(f)
@@ -460,7 +460,7 @@ def test_tile_compact_layout_is_bit_identical(name):
                 for f in case.outputs + [P.F_GRADU, P.F_U]:
                     gi, gb = c.download(f)
                     out[(variant, f)] = np.concatenate([gi, gb])
-            c.set_cell_kernel(2)
+            c.set_cell_kernel(1)
             c.interface_correct(c.interface_delta_n())
             for f in (P.F_GRADALPHA, P.F_CURVATURE):
                 gi, gb = c.download(f)
