@@ -115,7 +115,9 @@ enum {
     /* explicit part of turbulence.divDevRhoReff(rho, U) (fluid/UEqn.H:13; OpenFOAM linearViscousStress):
      * -fvc::div((rho*nuEff)*dev2(T(fvc::grad(U)))), laminar nuEff = thermo.nu()                      */
     SSAM_F_DIVDEVRHOREFF = 28, /* vector                                                              */
-    SSAM_F_COUNT = 29
+    SSAM_F_K1 = 29,         /* thermo.k1()  (incompressibleTwoPhaseThermalMixture.C:205-273)          */
+    SSAM_F_K2 = 30,         /* thermo.k2()  (:276-343)                                                */
+    SSAM_F_COUNT = 31
 };
 
 /* ---- model parameters (what the reference reads from dictionaries) ---------- */
@@ -293,6 +295,8 @@ SSAM_API ssam_status ssam_mixture_mu(ssam_ctx* ctx, const ssam_mixture_params* p
 SSAM_API ssam_status ssam_mixture_rho(ssam_ctx* ctx, const ssam_mixture_params* p);
 SSAM_API ssam_status ssam_mixture_cp(ssam_ctx* ctx, const ssam_mixture_params* p);
 SSAM_API ssam_status ssam_mixture_k(ssam_ctx* ctx, const ssam_mixture_params* p);
+/* k1() / k2(): the phase conductivity alone -> SSAM_F_K1 / SSAM_F_K2 (phase = 1 or 2) */
+SSAM_API ssam_status ssam_mixture_k_phase(ssam_ctx* ctx, const ssam_mixture_params* p, int phase);
 /* solver-side rho, rhoCp (multiRegionVoF/alphaEqnSubCycle.H:41-42) -> RHO_SOLVER, RHOCP */
 SSAM_API ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p);
 /* frictionModel::correct() -> stickModel::correct(): qvisc_, qfric_ (constantSlipStick.H:133-138,

@@ -42,7 +42,17 @@ Foam::stickModels::gpuStickBase::gpuStickBase
         IOobject("qfric", U_.time().timeName(), U_.mesh(), IOobject::MUST_READ, IOobject::AUTO_WRITE),
         U_.mesh()
     )
-{}
+{
+    ssamGpuMesh::New(U_.mesh()).setStickModel(this);
+}
+
+
+void Foam::stickModels::gpuStickBase::params(ssam_stick_params& p) const
+{
+    std::memset(&p, 0, sizeof(p));
+    fill(p);
+    p.fricPatch = U_.mesh().boundaryMesh().findPatchID(patch_);
+}
 
 
 void Foam::stickModels::gpuStickBase::gpuCorrect(bool withQfric)

@@ -36,6 +36,7 @@ Foam::viscosityModels::gpuViscoPlasticBase::gpuViscoPlasticBase
         dimensionedScalar("nu", dimViscosity, 0.0)
     )
 {
+    ssamGpuMesh::New(U_.mesh()).setViscModel(phase(), this);
     if (hasSigma)
     {
         sigmaf_ = autoPtr<volScalarField>(new volScalarField
@@ -71,12 +72,20 @@ void Foam::viscosityModels::gpuViscoPlasticBase::gpuCorrect()
         gpu.upload(SSAM_F_EPSDOT, mesh.lookupObject<volScalarField>("epsilonDotEq"));
     }
     gpu.check(ssam_viscosity_correct(gpu.ctx(), phase(), &p), "viscosityModel::correct");
+    if (p.model == SSAM_VISC_NORTON_HOFF) gpu.deviceWrote(SSAM_F_STRAINRATE);
     gpu.download(phase() == 1 ? SSAM_F_NU1 : SSAM_F_NU2, nu_);
     if (sigmaf_.valid())
     {
         gpu.download(SSAM_F_SIGMAF, sigmaf_());
         gpu.download(SSAM_F_SIGMAY, sigmay_());
     }
+}
+
+
+void Foam::viscosityModels::gpuViscoPlasticBase::params(ssam_viscosity_params& p) const
+{
+    std::memset(&p, 0, sizeof(p));
+    fill(p);
 }
 
 

@@ -18,9 +18,11 @@ from solidstateamfoam_b200 import params as P
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libssam_ref.so")
 _SO_GPU = os.path.join(_HERE, "_ref", "libssam_ref_gpu.so")  # same harness, GPU-backed viscosity models (integration/openfoam)
+_SO_GPU2 = os.path.join(_HERE, "_ref", "libssam_ref_gpu2.so")  # ... and the GPU-backed mixture translation unit
 REFERENCE_TREE = os.environ.get("SSAM_REFERENCE_TREE", "/root/reference")
 _lib = None
 _lib_gpu = None
+_lib_gpu2 = None
 
 
 def build_shim() -> bool:
@@ -30,6 +32,15 @@ def build_shim() -> bool:
         if r.returncode != 0:
             raise RuntimeError("building the OpenFOAM-shim demo failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
     return os.path.exists(_SO_GPU)
+
+
+def build_shim2() -> bool:
+    """oracle/_ref/libssam_ref_gpu2.so (Makefile target `shim2`): the mixture's own translation unit GPU-backed too"""
+    if os.path.isdir(REFERENCE_TREE) and not os.environ.get("SSAM_REF_NOBUILD"):
+        r = subprocess.run(["make", "-C", _HERE, "shim2", f"REF={REFERENCE_TREE}"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building the GPU-mixture shim failed:\n" + r.stdout[-3000:] + r.stderr[-3000:])
+    return os.path.exists(_SO_GPU2)
 
 
 def build() -> bool:
@@ -48,8 +59,14 @@ def available() -> bool:
         return False
 
 
-def lib(gpu: bool = False):
-    global _lib, _lib_gpu
+def lib(gpu=False):
+    global _lib, _lib_gpu, _lib_gpu2
+    if gpu == 2:
+        if _lib_gpu2 is None:
+            if not build_shim2():
+                raise RuntimeError("oracle/_ref/libssam_ref_gpu2.so is absent and there is no reference tree to build it from")
+            _lib_gpu2 = _bind(C.CDLL(_SO_GPU2))
+        return _lib_gpu2
     if gpu:
         if _lib_gpu is None:
             if not build_shim():
@@ -80,6 +97,11 @@ def _bind(L):
     L.ref_bc_rotational_slip.argtypes = [vp, C.c_char_p, dp]
     L.ref_calculate_strain.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp, dp]
     L.ref_set_U.argtypes = [vp, dp, C.POINTER(C.c_int32)]
+    if hasattr(L, "ref_gpu_traffic"):
+        L.ref_gpu_traffic.argtypes = [vp, dp, C.c_int]
+        L.ref_gpu_contexts.restype = C.c_int
+    if hasattr(L, "ref_teqn_update"):
+        L.ref_teqn_update.argtypes = [vp, C.c_int]
     return L
 
 
@@ -165,3 +187,16 @@ class ReferenceCase:
 
     def info(self) -> str:
         return self.L.ref_info(self.h).decode()
+
+    def teqn_update(self, fused: int = 0):
+        """fluid/TEqn.H:3-15 through integration/openfoam/ssamTEqnUpdate.H (GPU-mixture shim only)"""
+        self._chk(self.L.ref_teqn_update(self.h, fused))
+
+    def gpu_traffic(self, reset: bool = False):
+        """(bytes host->device, bytes device->host) the shim moved for this mesh since the last reset"""
+        out = np.zeros(2)
+        self.L.ref_gpu_traffic(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), 1 if reset else 0)
+        return int(out[0]), int(out[1])
+
+    def gpu_contexts(self) -> int:
+        return int(self.L.ref_gpu_contexts())

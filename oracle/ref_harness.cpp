@@ -312,4 +312,42 @@ int ref_calculate_strain(ref_case* h, double deltaT, const double* gradUIn, cons
     });
 }
 
+#ifdef SSAM_GPU_MIXTURE
+}  // extern "C"
+#include "ssamTEqnUpdate.H"
+extern "C" {
+
+// fluid/TEqn.H:3-15 through integration/openfoam/ssamTEqnUpdate.H on the case's own registered fields
+// ("epsilonDotEq", "muEff"; the results cpf / kf are registered as "cpf" / "kf").  fused = 0: the staged device-resident
+// sequence; 1: one ssam_update_fused with the TEqn outputs only; 2: ... with every output.
+int ref_teqn_update(ref_case* h, int fused) {
+    RefCase* c = RC(h);
+    return guarded(c, [&]() {
+        for (const char* nm : {"cpf", "kf"})
+            if (c->inputs.find(nm) == c->inputs.end()) {
+                volScalarField init(c->mesh, nm);
+                c->inputs[nm].reset(new volScalarField(IOobject(nm, "0", c->mesh, IOobject::NO_READ, IOobject::AUTO_WRITE), init));
+            }
+        volScalarField& eps = *c->inputs.at("epsilonDotEq");
+        volScalarField& muEff = *c->inputs.at("muEff");
+        if (fused)
+            ssamFusedUpdate(*c->U, *c->thermo, eps, muEff, *c->inputs.at("cpf"), *c->inputs.at("kf"), fused == 2);
+        else
+            ssamTEqnUpdate(*c->U, *c->thermo, c->friction.get(), eps, muEff, *c->inputs.at("cpf"), *c->inputs.at("kf"));
+    });
+}
+#endif
+
+#ifdef SSAM_WITH_GPU_SHIM
+// bytes the shim moved over PCIe for this case's mesh since the last reset: out[0] = host->device, out[1] = device->host
+void ref_gpu_traffic(ref_case* h, double* out, int reset) {
+    const ssamGpuMesh& gpu = ssamGpuMesh::New(RC(h)->mesh);
+    out[0] = double(gpu.bytesH2D());
+    out[1] = double(gpu.bytesD2H());
+    if (reset) gpu.resetTraffic();
+}
+// number of live GPU contexts (one per mesh / region)
+int ref_gpu_contexts() { return int(ssamGpuMesh::table().size()); }
+#endif
+
 }  // extern "C"

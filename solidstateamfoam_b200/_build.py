@@ -112,6 +112,8 @@ def build_oracle_ref(verbose: bool = False) -> str | None:
         if os.path.exists(os.path.join(LIB, "libssam_gpu.so")):
             # the drop-in demonstration: reference mixture / friction sources + integration/openfoam GPU models
             _run(["make", "-C", odir, "shim", f"REF={ref}"], verbose)
+            # ... and with the mixture's own translation unit GPU-backed as well (device-resident fields)
+            _run(["make", "-C", odir, "shim2", f"REF={ref}"], verbose)
     return so if os.path.exists(so) else None
 
 

@@ -21,7 +21,7 @@ SYMBOLS = [
     "ssam_abi_version", "ssam_launch_count", "ssam_set_cell_kernel", "ssam_set_cell_layout", "ssam_cell_layout_is_compact", "ssam_compact_cell_order", "ssam_profile_enable", "ssam_profile_get", "ssam_mesh_set", "ssam_patch_u_bc_set", "ssam_addressing_size",
     "ssam_addressing_get", "ssam_field_upload", "ssam_field_download", "ssam_field_device_ptr", "ssam_field_is_set",
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
-    "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k",
+    "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k", "ssam_mixture_k_phase",
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_div_dev_rho_reff_explicit", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
     "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
@@ -98,6 +98,7 @@ def load():
     L.ssam_mixture_muf.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_mixture_nuf.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_field_min_max.argtypes = [vp, C.c_int, dp, dp]
+    L.ssam_mixture_k_phase.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
     L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
@@ -282,6 +283,10 @@ class Context:
 
     def mixture(self, what: str, p: P.MixtureParams):
         self._chk(getattr(self.L, "ssam_mixture_" + what)(self.h, C.byref(p)))
+
+    def mixture_k_phase(self, p: P.MixtureParams, phase: int):
+        """k1() / k2() -> F_K1 / F_K2"""
+        self._chk(self.L.ssam_mixture_k_phase(self.h, C.byref(p), phase))
 
     def solver_rho_rhocp(self, p: P.MixtureParams):
         self._chk(self.L.ssam_solver_rho_rhocp(self.h, C.byref(p)))

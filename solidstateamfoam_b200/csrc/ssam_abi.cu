@@ -2118,6 +2118,23 @@ ssam_status ssam_mixture_k(ssam_ctx* ctx, const ssam_mixture_params* p) {
     return finish(ctx);
 }
 
+ssam_status ssam_mixture_k_phase(ssam_ctx* ctx, const ssam_mixture_params* p, int phase) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
+    CHECK(ctx && p && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set / null params");
+    CHECK(phase == 1 || phase == 2, SSAM_ERR_INVALID, "phase must be 1 or 2");
+    TRY(need(ctx, SSAM_F_T, "temp"));
+    const int out = phase == 1 ? SSAM_F_K1 : SSAM_F_K2;
+    TRY(ensureField(ctx, out));
+    KPhaseStage st;
+    st.kc = phase == 1 ? p->k1 : p->k2;
+    TRY(unitsShift(ctx, st.kc, &st.shift));
+    st.T = ctx->plane[SSAM_F_T][0];
+    st.k = ctx->plane[out][0];
+    LAUNCH((k_map<KPhaseStage>), mapGrid(ctx), 256, ctx->nTot, st);
+    ctx->isSet[out] = true;
+    return finish(ctx);
+}
+
 ssam_status ssam_solver_rho_rhocp(ssam_ctx* ctx, const ssam_mixture_params* p) {
     if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
     CHECK(ctx && p, SSAM_ERR_INVALID, "null argument");
