@@ -334,10 +334,24 @@ enum {
     SSAM_FF_MUF = 1,   /* incompressibleTwoPhaseThermalMixture::muf()  (…Mixture.C:163-180)              */
     SSAM_FF_NUF = 2,   /* incompressibleTwoPhaseThermalMixture::nuf()  (…Mixture.C:183-202)              */
     SSAM_FF_KF = 3,    /* fvc::interpolate(kf): the face conductivity fvm::laplacian(kf, temp) uses (fluid/TEqn.H:22)  */
-    SSAM_FF_COUNT = 4
+    SSAM_FF_PHI = 4,   /* the face flux phi, IN (ssam_face_field_upload)                                            */
+    SSAM_FF_PHIC = 5,  /* the alpha-equation compression coefficient phic (multiRegionVoF/alphaEqn.H:58-87)          */
+    SSAM_FF_COUNT = 6
 };
 SSAM_API ssam_status ssam_face_field_download(ssam_ctx* ctx, int face_field, double* internal_faces,
                                               double* boundary_faces);
+/* surfaceScalarField -> device slot (inputs such as the face flux phi): nInternalFaces + nBoundaryFaces values */
+SSAM_API ssam_status ssam_face_field_upload(ssam_ctx* ctx, int which, const double* internal_faces,
+                                            const double* boundary_faces);
+/* The interface-compression coefficient of the alpha equation (multiRegionVoF/alphaEqn.H:58-87) -> SSAM_FF_PHIC:
+ *   phic = cAlpha*mag(phi/magSf)
+ *   icAlpha > 0:  phic *= (1 - icAlpha);  phic += (cAlpha*icAlpha)*fvc::interpolate(mag(U))            (:61-65)
+ *   scAlpha > 0:  phic += scAlpha*mag(mesh.delta() & fvc::interpolate(symm(fvc::grad(U))))             (:68-72)
+ *   phic = 0 on non-coupled boundary faces                                                            (:79-87)
+ * Needs SSAM_FF_PHI, SSAM_F_U (icAlpha > 0) and SSAM_F_GRADU incl. its boundary / processor values (scAlpha > 0:
+ * call ssam_grad_u first).  magSf = mag(Sf), mesh.delta() = C[neighbour] - C[owner] on internal faces and the
+ * cell-to-cell vector across processor faces (neighbour cell centres exchanged once per mesh). */
+SSAM_API ssam_status ssam_alpha_compression_coeff(ssam_ctx* ctx, double cAlpha, double icAlpha, double scAlpha);
 SSAM_API double* ssam_face_field_device_ptr(ssam_ctx* ctx, int face_field);
 /* muf()/nuf(): alpha1f = min(max(fvc::interpolate(alpha1),0),1);
  *   muf = alpha1f*rho1*interpolate(nu1) + (1-alpha1f)*rho2*interpolate(nu2);  nuf = muf/(alpha1f*rho1+(1-alpha1f)*rho2)

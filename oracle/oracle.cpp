@@ -62,6 +62,8 @@ struct Case {
     bool addrBuilt = false;
     Fld nHatf;  // surfaceScalarField: internal faces then boundary faces
     Fld muf, nuf;
+    Fld phi, phic;     // face flux (input) and the alphaEqn.H compression coefficient
+    Fld procNbrC;      // [3*nBnd] cell centre of the neighbour rank's cell behind each processor face (else 0)
 };
 
 int ncompOf(int field) {
@@ -949,6 +951,93 @@ int interfaceCorrect(Case& c, double deltaN, int stage) {
 }
 
 // ================================================================================================
+// multiRegionVoF/alphaEqn.H:58-87 -- the interface-compression coefficient of the alpha equation:
+//     surfaceScalarField phic(thermo.cAlpha()*mag(phi/mesh.magSf()));                                   :58
+//     if (icAlpha > 0) { phic *= (1.0 - icAlpha);                                                       :63
+//                        phic += (thermo.cAlpha()*icAlpha)*fvc::interpolate(mag(U)); }                  :64
+//     if (scAlpha > 0) { phic += scAlpha*mag(mesh.delta() & fvc::interpolate(symm(fvc::grad(U)))); }    :70-71
+//     non-coupled boundary patches: phic == 0                                                           :79-87
+// OpenFOAM pieces restated (PARITY UNPINNED): magSf = mag(Sf) (+ VSMALL, fvMesh::makeMagSf);
+// linear interpolation per component; symm(T) per SymmTensorI.H; Vector & SymmTensor =
+// (v.x*xx + v.y*xy + v.z*xz, v.x*xy + v.y*yy + v.z*yz, v.x*xz + v.y*yz + v.z*zz); mesh.delta(): internal faces
+// C[neighbour] - C[owner], processor faces (Cf - Cn) - (nbrCf - nbrCn) (processorFvPatch::delta()).
+// Inputs: phi (face flux), U incl. boundary values, GRADU incl. boundary values (scAlpha > 0), the neighbour cell
+// centres of the processor faces (c.procNbrC, orc_exchange_cell_centres).
+// ================================================================================================
+int alphaCompressionCoeff(Case& c, double cAlpha, double icAlpha, double scAlpha) {
+    if (c.phi.size() != size_t(c.nFaces)) {
+        c.err = "phi not set";
+        return SSAM_ERR_MISSING_FIELD;
+    }
+    if ((icAlpha > 0 && !c.set[SSAM_F_U]) || (scAlpha > 0 && !c.set[SSAM_F_GRADU])) {
+        c.err = "U / gradU not set";
+        return SSAM_ERR_MISSING_FIELD;
+    }
+    const int32_t nC = c.nCells;
+    auto magSfOf = [&](int32_t f) {
+        const double* S = &c.Sf[3 * size_t(f)];
+        return std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]) + VSMALL;
+    };
+    Fld phic(c.nFaces);
+    for (int32_t f = 0; f < c.nFaces; ++f) phic[f] = cAlpha * std::fabs(c.phi[f] / magSfOf(f));
+    auto coupled = [&](int p) { return c.patchKind[p] == SSAM_PATCH_PROCESSOR; };
+    if (icAlpha > 0) {
+        const Fld& U = c.f[SSAM_F_U];
+        Fld magU(c.nTot);
+        for (int32_t i = 0; i < c.nTot; ++i) magU[i] = magVec(U[3 * size_t(i)], U[3 * size_t(i) + 1], U[3 * size_t(i) + 2]);
+        const Fld magUf = interpolateLinear(c, magU);
+        const double s = cAlpha * icAlpha;
+        for (int32_t f = 0; f < c.nFaces; ++f) {
+            phic[f] *= (1.0 - icAlpha);
+            phic[f] += s * magUf[f];
+        }
+    }
+    if (scAlpha > 0) {
+        const Fld& G = c.f[SSAM_F_GRADU];
+        auto symmOf = [&](int32_t i, double* S6) {  // xx, xy, xz, yy, yz, zz
+            const double* g = &G[9 * size_t(i)];
+            S6[0] = g[0]; S6[1] = 0.5 * (g[1] + g[3]); S6[2] = 0.5 * (g[2] + g[6]);
+            S6[3] = g[4]; S6[4] = 0.5 * (g[5] + g[7]); S6[5] = g[8];
+        };
+        auto term = [&](const double* d, const double* S6) {
+            const double vx = d[0] * S6[0] + d[1] * S6[1] + d[2] * S6[2];
+            const double vy = d[0] * S6[1] + d[1] * S6[3] + d[2] * S6[4];
+            const double vz = d[0] * S6[2] + d[1] * S6[4] + d[2] * S6[5];
+            return scAlpha * magVec(vx, vy, vz);
+        };
+        for (int32_t f = 0; f < c.nIF; ++f) {
+            double sP[6], sN[6], sf[6], d[3];
+            symmOf(c.owner[f], sP);
+            symmOf(c.neighbour[f], sN);
+            for (int k = 0; k < 6; ++k) sf[k] = c.w[f] * (sP[k] - sN[k]) + sN[k];
+            for (int k = 0; k < 3; ++k) d[k] = c.C[3 * size_t(c.neighbour[f]) + k] - c.C[3 * size_t(c.owner[f]) + k];
+            phic[f] += term(d, sf);
+        }
+        for (int p = 0; p < c.nPatches; ++p) {
+            if (!coupled(p)) continue;  // the others are zeroed below
+            for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) {
+                const int32_t b = f - c.nIF, P = c.owner[f];
+                double sP[6], sB[6], sf[6], d[3];
+                symmOf(P, sP);
+                symmOf(nC + b, sB);
+                for (int k = 0; k < 6; ++k) sf[k] = c.w[f] * sP[k] + (1.0 - c.w[f]) * sB[k];
+                for (int k = 0; k < 3; ++k) {
+                    const double cf = c.Cf_b[3 * size_t(b) + k];
+                    d[k] = (cf - c.C[3 * size_t(P) + k]) - (cf - (c.procNbrC.empty() ? 0.0 : c.procNbrC[3 * size_t(b) + k]));
+                }
+                phic[f] += term(d, sf);
+            }
+        }
+    }
+    for (int p = 0; p < c.nPatches; ++p) {
+        if (coupled(p)) continue;
+        for (int32_t f = c.patchStart[p]; f < c.patchStart[p] + c.patchSize[p]; ++f) phic[f] = 0.0;
+    }
+    c.phic.swap(phic);
+    return 0;
+}
+
+// ================================================================================================
 // Explicit part of turbulence.divDevRhoReff(rho, U) (fluid/UEqn.H:13).  OpenFOAM v1806 library code
 // (linearViscousStress<BasicTurbulenceModel>::divDevRhoReff), restated -- PARITY UNPINNED:
 //     - fvc::div((alpha*rho*nuEff())*dev2(T(fvc::grad(U))))        [- fvm::laplacian(...) stays in OpenFOAM]
@@ -1284,6 +1373,37 @@ void orc_field_min_max(orc_case** cases, int nRanks, int field, double* mn, doub
     *mx = hi;
 }
 int orc_div_dev_rho_reff_explicit(orc_case* h) { return divDevRhoReffExplicit(CASE(h)); }
+int orc_set_phi(orc_case* h, const double* phi) {
+    Case& c = CASE(h);
+    c.phi.assign(phi, phi + c.nFaces);
+    return 0;
+}
+int orc_alpha_compression_coeff(orc_case* h, double cAlpha, double icAlpha, double scAlpha) {
+    return alphaCompressionCoeff(CASE(h), cAlpha, icAlpha, scAlpha);
+}
+double* orc_phic(orc_case* h) { return CASE(h).phic.data(); }
+// processorPolyPatch::neighbFaceCellCentres(): the cell centre behind each processor face on the neighbour rank
+int orc_exchange_cell_centres(orc_case** cases, int nRanks) {
+    for (int r = 0; r < nRanks; ++r) {
+        Case& me = CASE(cases[r]);
+        me.procNbrC.assign(size_t(me.nBnd) * 3, 0.0);
+        for (int p = 0; p < me.nPatches; ++p) {
+            if (me.patchKind[p] != SSAM_PATCH_PROCESSOR) continue;
+            const int q = me.patchNbrRank[p];
+            if (q < 0 || q >= nRanks) return SSAM_ERR_COMM;
+            Case& nb = CASE(cases[q]);
+            int pq = -1;
+            for (int pp = 0; pp < nb.nPatches; ++pp)
+                if (nb.patchKind[pp] == SSAM_PATCH_PROCESSOR && nb.patchNbrRank[pp] == r) pq = pp;
+            if (pq < 0 || nb.patchSize[pq] != me.patchSize[p]) return SSAM_ERR_COMM;
+            for (int32_t i = 0; i < me.patchSize[p]; ++i) {
+                const int32_t b = me.patchStart[p] - me.nIF + i, nbrCell = nb.owner[nb.patchStart[pq] + i];
+                for (int k = 0; k < 3; ++k) me.procNbrC[size_t(b) * 3 + k] = nb.C[size_t(nbrCell) * 3 + k];
+            }
+        }
+    }
+    return 0;
+}
 int orc_interface_correct(orc_case* h, double deltaN, int stage) { return interfaceCorrect(CASE(h), deltaN, stage); }
 double* orc_interface_nhatf(orc_case* h) { return CASE(h).nHatf.data(); }
 double orc_interface_delta_n(orc_case** cases, int nRanks) {

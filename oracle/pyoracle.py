@@ -55,6 +55,11 @@ def lib():
         L.orc_interface_correct.argtypes = [vp, C.c_double, C.c_int]
         L.orc_interface_nhatf.restype = dp
         L.orc_interface_nhatf.argtypes = [vp]
+        L.orc_set_phi.argtypes = [vp, dp]
+        L.orc_alpha_compression_coeff.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+        L.orc_phic.restype = dp
+        L.orc_phic.argtypes = [vp]
+        L.orc_exchange_cell_centres.argtypes = [C.POINTER(vp), C.c_int]
         L.orc_interface_delta_n.restype = C.c_double
         L.orc_interface_delta_n.argtypes = [C.POINTER(vp), C.c_int]
         L.orc_friction_patch_sums.argtypes = [vp, C.c_int, dp]
@@ -157,6 +162,14 @@ class OracleCase:
         """interfaceProperties::correct(); stage 1 = cell gradient, 2 = the rest (halo steps go in between)."""
         self._chk(lib().orc_interface_correct(self.h, deltaN, stage))
 
+    def alpha_compression_coeff(self, phi, cAlpha, icAlpha, scAlpha):
+        """multiRegionVoF/alphaEqn.H:58-87: phic from the face flux phi [nFaces], U and GRADU -> [nFaces]"""
+        ph = np.ascontiguousarray(phi, dtype=np.float64)
+        assert ph.shape == (self.mesh.nFaces,)
+        lib().orc_set_phi(self.h, ph.ctypes.data_as(C.POINTER(C.c_double)))
+        self._chk(lib().orc_alpha_compression_coeff(self.h, cAlpha, icAlpha, scAlpha))
+        return np.ctypeslib.as_array(lib().orc_phic(self.h), shape=(self.mesh.nFaces,)).copy()
+
     def nhatf(self):
         return np.ctypeslib.as_array(lib().orc_interface_nhatf(self.h), shape=(self.mesh.nFaces,)).copy()
 
@@ -207,6 +220,14 @@ def halo_exchange(cases, field):
     st = lib().orc_halo_exchange(arr, len(cases), field)
     if st:
         raise OracleError(st, "halo exchange: processor patches do not match")
+
+
+def exchange_cell_centres(cases):
+    """processorPolyPatch::neighbFaceCellCentres() for every rank (needed by mesh.delta() on processor faces)"""
+    arr = (C.c_void_p * len(cases))(*[c.h for c in cases])
+    st = lib().orc_exchange_cell_centres(arr, len(cases))
+    if st:
+        raise OracleError(st, "cell-centre exchange: processor patches do not match")
 
 
 def field_min_max(cases, field):

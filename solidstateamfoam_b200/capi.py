@@ -23,7 +23,7 @@ SYMBOLS = [
     "ssam_bc_rotational_slip", "ssam_grad_u", "ssam_strain_rate", "ssam_viscosity_correct", "ssam_mixture_calc_nu",
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k", "ssam_mixture_k_phase",
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_div_dev_rho_reff_explicit", "ssam_interface_correct",
-    "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download",
+    "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download", "ssam_face_field_upload", "ssam_alpha_compression_coeff",
     "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_measure_fp64_peak", "ssam_comm_unique_id", "ssam_comm_init", "ssam_comm_init_local", "ssam_halo_exchange", "ssam_halo_transport", "ssam_halo_bytes_last_update",
 ]
@@ -99,6 +99,8 @@ def load():
     L.ssam_mixture_nuf.argtypes = [vp, C.POINTER(P.MixtureParams)]
     L.ssam_field_min_max.argtypes = [vp, C.c_int, dp, dp]
     L.ssam_mixture_k_phase.argtypes = [vp, C.POINTER(P.MixtureParams), C.c_int]
+    L.ssam_face_field_upload.argtypes = [vp, C.c_int, dp, dp]
+    L.ssam_alpha_compression_coeff.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
@@ -313,6 +315,17 @@ class Context:
         bi = out[n_internal_faces:]
         self._chk(self.L.ssam_face_field_download(self.h, which, _dptr(out), _dptr(bi) if n_boundary_faces else None))
         return out
+
+    def face_field_upload(self, which: int, values):
+        """surfaceScalarField [nFaces] (internal faces, then boundary faces) -> device slot"""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        nif = self.mesh.nInternalFaces
+        assert v.shape == (self.mesh.nFaces,)
+        self._chk(self.L.ssam_face_field_upload(self.h, which, _dptr(v), _dptr(v[nif:]) if self.nBnd else None))
+
+    def alpha_compression_coeff(self, cAlpha: float, icAlpha: float, scAlpha: float):
+        """multiRegionVoF/alphaEqn.H:58-87 -> FF_PHIC"""
+        self._chk(self.L.ssam_alpha_compression_coeff(self.h, cAlpha, icAlpha, scAlpha))
 
     def face_interpolate(self, field: int, face_field: int):
         """fvc::interpolate(field) (linear) -> face field slot"""

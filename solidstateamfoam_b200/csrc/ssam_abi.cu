@@ -77,6 +77,8 @@ struct ssam_ctx {
     double* faceField[SSAM_FF_COUNT] = {nullptr};  // surfaceScalarFields (nFaces values each), lazily allocated
     bool faceFieldSet[SSAM_FF_COUNT] = {false};
     double* minmaxScratch = nullptr;
+    double* procNbrC[3] = {nullptr, nullptr, nullptr};  // [nBnd] neighbour-rank cell centre behind each processor face
+    bool procNbrCSet = false;
     double sumV = 0.0;        // sequential sum of the cell volumes (deltaN_)
 
     double* plane[SSAM_F_COUNT][9] = {{nullptr}};
@@ -86,7 +88,10 @@ struct ssam_ctx {
     size_t stageCap = 0;
 
     int fricPatchCached = -1;
-    int fricLocalFor = -1;  // in-process group: patch whose LOCAL sums fricSums[0..3] currently hold
+    // boundary-face centres and areas as given by the caller: the friction-patch sums of an in-process rank group are
+    // formed on the host (pure mesh geometry; no device synchronisation inside a collective update)
+    std::vector<double> hostCfB, hostMagSfB;
+    double fricHost[4] = {0, 0, 0, 0};
     double* fricSums = nullptr;  // device: [0..3] local sums, [4..7] cross-rank sums
     int qfricZeroedFor = -2;
     bool nu2Filled = false;
@@ -270,6 +275,8 @@ void freeMesh(ssam_ctx* c) {
         c->faceFieldSet[k] = false;
     }
     devFree(c->minmaxScratch);
+    for (auto& q : c->procNbrC) devFree(q);
+    c->procNbrCSet = false;
     devFree(c->magSf_b);
     devFree(c->deltaCoeffs_b);
     for (auto& p : c->Cpl) devFree(p);
@@ -287,7 +294,8 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->cellFaces);
     devFree(c->faceColour);
     c->fricPatchCached = -1;
-    c->fricLocalFor = -1;
+    c->hostCfB.clear();
+    c->hostMagSfB.clear();
     c->qfricZeroedFor = -2;
     c->nu2Filled = false;
     c->haveMesh = false;
@@ -743,26 +751,6 @@ ssam_status p2pSetupLocal(ssam_ctx* ctx) {
     P.state = 1;
     return SSAM_OK;
 }
-// sum of `n` doubles over the ranks of an in-process group, in rank order (host side; tiny and rare)
-ssam_status localAllReduce(ssam_ctx* ctx, double* dev, int n, int op /* 0 sum, 1 min, 2 max */,
-                           double* (*where)(ssam_ctx*)) {
-    std::vector<double> acc(size_t(n), 0.0), tmp(static_cast<size_t>(n));
-    for (size_t r = 0; r < ctx->localPeers.size(); ++r) {
-        ssam_ctx* q = ctx->localPeers[r];
-        CU(cudaSetDevice(q->device));
-        CU(cudaStreamSynchronize(q->stream));
-        CU(cudaMemcpy(tmp.data(), where(q), size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < n; ++k)
-            acc[size_t(k)] = r == 0 ? tmp[size_t(k)]
-                                    : (op == 0 ? acc[size_t(k)] + tmp[size_t(k)]
-                                               : (op == 1 ? std::min(acc[size_t(k)], tmp[size_t(k)]) : std::max(acc[size_t(k)], tmp[size_t(k)])));
-    }
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaMemcpyAsync(dev, acc.data(), size_t(n) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    return SSAM_OK;
-}
-
 ssam_status ensureHaloTransport(ssam_ctx* ctx) {
     if (ctx->nProcPatches == 0 || ctx->p2p.state != 0) return SSAM_OK;
     if (!ctx->localPeers.empty()) return p2pSetupLocal(ctx);
@@ -831,6 +819,53 @@ ssam_status haloExchangeFields(ssam_ctx* ctx, const int* fields, int nFields, cu
 }
 ssam_status haloExchangeField(ssam_ctx* ctx, int field) { return haloExchangeFields(ctx, &field, 1, ctx->stream); }
 
+// The same exchange for data that is not a field: gather plSend[k][faceCells], deliver into plRecv[k][nCells + b]
+// (pass plRecv[k] = array - nCells to receive into a boundary-sized array).  Used once per mesh for the neighbour
+// cell centres (processorPolyPatch::neighbFaceCellCentres()).
+ssam_status haloExchangePlanes(ssam_ctx* ctx, const PlanePtrs& plSend, const PlanePtrs& plRecv, int nc, cudaStream_t stream) {
+    if (ctx->nProcPatches == 0) return SSAM_OK;
+    CHECK(ctx->comm != nullptr || !ctx->localPeers.empty(), SSAM_ERR_COMM,
+          "mesh has processor patches but ssam_comm_init was not called");
+    CHECK(ctx->localPeers.empty() || !ctx->blocking, SSAM_ERR_INVALID,
+          "in-process rank group: collective calls need ssam_set_blocking(ctx, 0) on every rank (enqueue all ranks, "
+          "then synchronise)");
+    TRY(ensureHaloTransport(ctx));
+    if (ctx->p2p.state == 1) {
+        unsigned long long seq = 0;
+        TRY(haloPushPeer(ctx, plSend, nc, stream, &seq));
+        return haloWaitUnpackPeer(ctx, plRecv, nc, seq, stream);
+    }
+    const size_t needBuf = size_t(ctx->nProcFaces) * 16;
+    if (ctx->sendCap < needBuf) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        devFree(ctx->sendBuf);
+        TRY(devAlloc(ctx, &ctx->sendBuf, needBuf));
+        ctx->sendCap = needBuf;
+    }
+    HaloLayout L;
+    L.nPatches = ctx->nProcPatches;
+    for (int p = 0; p <= ctx->nProcPatches; ++p) L.offsets[p] = ctx->haloOffsets[p];
+    k_halo_pack<<<gridFor((long long)ctx->nProcFaces * nc, 256), 256, 0, stream>>>(ctx->haloSendCells, L, nc, plSend,
+                                                                                    ctx->sendBuf);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    NcclApi& N = nccl();
+    NC(N.GroupStart());
+    for (int p = 0; p < ctx->nProcPatches; ++p) {
+        const int patch = ctx->haloPatch[p];
+        const int peer = ctx->patchNbrRank[patch];
+        const int off = ctx->haloOffsets[p], np = ctx->haloOffsets[p + 1] - off;
+        const int b0 = ctx->patchStart[patch] - ctx->nIF;
+        for (int k = 0; k < nc; ++k) {
+            NC(N.Send(ctx->sendBuf + size_t(nc) * off + size_t(k) * np, np, ncclFloat64, peer, ctx->comm, stream));
+            NC(N.Recv(plRecv.p[k] + ctx->nCells + b0, np, ncclFloat64, peer, ctx->comm, stream));
+        }
+    }
+    NC(N.GroupEnd());
+    ctx->launches++;
+    return SSAM_OK;
+}
+
 ssam_status ensureFricSums(ssam_ctx* ctx, int patch) {
     if (ctx->fricPatchCached == patch) return SSAM_OK;
     if (!ctx->fricSums) TRY(devAlloc(ctx, &ctx->fricSums, 8));
@@ -838,23 +873,24 @@ ssam_status ensureFricSums(ssam_ctx* ctx, int patch) {
     LAUNCH(k_patch_sums, 1, 32, b0, ctx->patchSize[patch], ctx->Cpl[0], ctx->Cpl[1], ctx->Cpl[2], ctx->magSf_b,
            ctx->nCells, ctx->fricSums);
     if (!ctx->localPeers.empty() && ctx->nRanks > 1) {
-        // in-process group: every rank's local sums (computed here for the ranks that have not needed them yet)
-        for (ssam_ctx* q : ctx->localPeers) {
-            if (q == ctx || q->fricLocalFor == patch) continue;
+        // in-process group: the ranks' sums (constantSlipStick.C:118-131, serial face order, area starting at VSMALL on
+        // every rank like the reference) formed on the host from the caller's geometry and added in rank order
+        double tot[4] = {0, 0, 0, 0};
+        for (size_t r = 0; r < ctx->localPeers.size(); ++r) {
+            const ssam_ctx* q = ctx->localPeers[r];
             CHECK(q->haveMesh && patch < q->nPatches, SSAM_ERR_COMM, "in-process group: neighbour rank has no such patch");
-            CU(cudaSetDevice(q->device));
-            if (!q->fricSums) {
-                ssam_status st = devAlloc(q, &q->fricSums, 8);
-                if (st != SSAM_OK) return fail(ctx, st, q->err);
+            double c[3] = {0.0, 0.0, 0.0}, a = 1e-300;
+            const int b0 = q->patchStart[size_t(patch)] - q->nIF;
+            for (int i = 0; i < q->patchSize[size_t(patch)]; ++i) {
+                const double ms = q->hostMagSfB[size_t(b0 + i)];
+                for (int k = 0; k < 3; ++k) c[k] += q->hostCfB[3 * size_t(b0 + i) + size_t(k)] * ms;
+                a += ms;
             }
-            k_patch_sums<<<1, 32, 0, q->stream>>>(q->patchStart[size_t(patch)] - q->nIF, q->patchSize[size_t(patch)], q->Cpl[0],
-                                                  q->Cpl[1], q->Cpl[2], q->magSf_b, q->nCells, q->fricSums);
-            q->launches++;
-            q->fricLocalFor = patch;
+            const double loc[4] = {c[0], c[1], c[2], a};
+            for (int k = 0; k < 4; ++k) tot[k] = r == 0 ? loc[k] : tot[k] + loc[k];
         }
-        CU(cudaSetDevice(ctx->device));
-        ctx->fricLocalFor = patch;
-        TRY(localAllReduce(ctx, ctx->fricSums + 4, 4, 0, [](ssam_ctx* q) { return q->fricSums; }));
+        for (int k = 0; k < 4; ++k) ctx->fricHost[k] = tot[k];
+        CU(cudaMemcpyAsync(ctx->fricSums + 4, ctx->fricHost, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     } else if (ctx->comm && ctx->nRanks > 1) {
         // reduce(patchCenter_, sumOp<vector>()); reduce(patchArea_, sumOp<scalar>())  (constantSlipStick.C:134-135)
         // NB every rank starts its area at VSMALL like the reference does.
@@ -1694,6 +1730,8 @@ static ssam_status meshSetImpl(ssam_ctx* ctx, const ssam_mesh_desc* m) {
     TRY(devAlloc(ctx, &ctx->deltaCoeffs_b, nB));
     if (nB) {
         CHECK(m->Cf_b && m->magSf_b && m->deltaCoeffs_b, SSAM_ERR_INVALID, "null boundary geometry");
+        ctx->hostCfB.assign(m->Cf_b, m->Cf_b + 3 * nB);
+        ctx->hostMagSfB.assign(m->magSf_b, m->magSf_b + nB);
         CU(cudaMemcpyAsync(ctx->magSf_b, m->magSf_b, nB * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->deltaCoeffs_b, m->deltaCoeffs_b, nB * sizeof(double), cudaMemcpyHostToDevice,
                            ctx->stream));
@@ -2296,6 +2334,76 @@ ssam_status ssam_face_field_download(ssam_ctx* ctx, int ff, double* internal_fac
                            ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return SSAM_OK;
+}
+
+ssam_status ssam_face_field_upload(ssam_ctx* ctx, int ff, const double* internal_faces, const double* boundary_faces) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
+    CHECK(ctx && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    CHECK(ff >= 0 && ff < SSAM_FF_COUNT, SSAM_ERR_INVALID, "bad face-field id");
+    TRY(ensureFaceField(ctx, ff));
+    if (internal_faces && ctx->nIF) {
+        if (ctx->faceKey) {  // tile-compact layout: device face g holds the caller's face faceKey[g]
+            TRY(ensureStage(ctx, size_t(ctx->nIF)));
+            CU(cudaMemcpyAsync(ctx->stage, internal_faces, size_t(ctx->nIF) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH(k_gather_by_key, gridFor(ctx->nIF, 256), 256, ctx->stage, ctx->faceKey, ctx->nIF, ctx->faceField[ff]);
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            CU(cudaMemcpyAsync(ctx->faceField[ff], internal_faces, size_t(ctx->nIF) * sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->stream));
+        }
+    }
+    if (boundary_faces && ctx->nBnd)
+        CU(cudaMemcpyAsync(ctx->faceField[ff] + ctx->nIF, boundary_faces, size_t(ctx->nBnd) * sizeof(double),
+                           cudaMemcpyHostToDevice, ctx->stream));
+    ctx->faceFieldSet[ff] = true;
+    return finish(ctx);
+}
+
+ssam_status ssam_alpha_compression_coeff(ssam_ctx* ctx, double cAlpha, double icAlpha, double scAlpha) {
+    if (ctx) cudaSetDevice(ctx->device);  // every entry point runs on the context's own GPU
+    CHECK(ctx && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set");
+    CHECK(ctx->faceFieldSet[SSAM_FF_PHI], SSAM_ERR_MISSING_FIELD, "field not available: phi (ssam_face_field_upload)");
+    if (icAlpha > 0) TRY(need(ctx, SSAM_F_U, "U"));
+    if (scAlpha > 0) TRY(need(ctx, SSAM_F_GRADU, "gradU (call ssam_grad_u first)"));
+    TRY(ensureFaceField(ctx, SSAM_FF_PHIC));
+    if (scAlpha > 0 && ctx->nProcPatches > 0 && !ctx->procNbrCSet) {
+        // processorPolyPatch::neighbFaceCellCentres(), once per mesh
+        PlanePtrs snd, rcv;
+        for (int k = 0; k < 16; ++k) snd.p[k] = rcv.p[k] = nullptr;
+        for (int k = 0; k < 3; ++k) {
+            if (!ctx->procNbrC[k]) {
+                TRY(devAlloc(ctx, &ctx->procNbrC[k], size_t(ctx->nBnd)));
+                CU(cudaMemsetAsync(ctx->procNbrC[k], 0, size_t(ctx->nBnd) * sizeof(double), ctx->stream));
+            }
+            snd.p[k] = ctx->Cpl[k];
+            rcv.p[k] = ctx->procNbrC[k] - ctx->nCells;
+        }
+        TRY(haloExchangePlanes(ctx, snd, rcv, 3, ctx->stream));
+        ctx->procNbrCSet = true;
+    }
+    PhicArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.nCells = ctx->nCells;
+    a.nIF = ctx->nIF;
+    a.nBnd = ctx->nBnd;
+    a.geo = ctx->geo;
+    a.owner = ctx->owner;
+    a.neighbour = ctx->neighbour;
+    a.bndFlags = ctx->bndFlags;
+    for (int k = 0; k < 3; ++k) {
+        a.C[k] = ctx->Cpl[k];
+        a.nbrC[k] = ctx->procNbrC[k];
+        a.U[k] = ctx->plane[SSAM_F_U][k];
+    }
+    for (int k = 0; k < 9; ++k) a.g[k] = ctx->plane[SSAM_F_GRADU][k];
+    a.phi = ctx->faceField[SSAM_FF_PHI];
+    a.phic = ctx->faceField[SSAM_FF_PHIC];
+    a.cAlpha = cAlpha;
+    a.icAlpha = icAlpha;
+    a.scAlpha = scAlpha;
+    LAUNCH(k_phic, gridFor(ctx->nFaces, 256), 256, a);
+    ctx->faceFieldSet[SSAM_FF_PHIC] = true;
+    return finish(ctx);
 }
 
 double* ssam_face_field_device_ptr(ssam_ctx* ctx, int ff) {
@@ -2944,7 +3052,6 @@ ssam_status ssam_comm_init_local(ssam_ctx** ctxs, int nRanks) {
         c->rank = r;
         c->nRanks = nRanks;
         c->fricPatchCached = -1;
-        c->fricLocalFor = -1;
         p2pFree(c);
     }
     return SSAM_OK;

@@ -15,7 +15,7 @@ F_PRGH, F_Z, F_SIGMAF_PP, F_DEPSEQ, F_EPSEQ, F_SIGMAVM = range(20, 26)
 F_GRADALPHA, F_CURVATURE, F_DIVDEVRHOREFF = 26, 27, 28
 F_K1, F_K2 = 29, 30
 F_COUNT = 31
-FF_NHATF, FF_MUF, FF_NUF, FF_KF = range(4)
+FF_NHATF, FF_MUF, FF_NUF, FF_KF, FF_PHI, FF_PHIC = range(6)
 FIELD_NAMES = ["U", "temp", "alpha1", "p", "epsilonDotEq", "nu1", "nu2", "sigmaf", "sigmay", "nu", "muEff", "rho",
                "cp", "k", "qvisc", "qfric", "gradU", "strainRate", "rhoSolver", "rhoCp", "p_rgh", "Z", "sigmafPP",
                "dEpsilonEq", "epsilonEq", "sigmavm", "gradAlpha", "interfaceProperties:K", "divDevRhoReffExplicit", "k1", "k2"]

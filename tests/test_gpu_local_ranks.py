@@ -69,6 +69,25 @@ def test_in_process_rank_group_matches_the_decomposed_oracle(n_ranks, decomp):
         for r, (ctx, oc) in enumerate(zip(ctxs, ocs)):
             gi, gb = ctx.download(P.F_GRADU)
             check_field(f"rank{r} staged gradU", np.concatenate([gi, gb]), oc.field(P.F_GRADU), True)
+        # alphaEqn.H:58-87 on processor faces: interpolation with the neighbour rank's U / gradU, mesh.delta() from the
+        # neighbour cell centres exchanged once per mesh
+        O.halo_exchange(ocs, P.F_U)
+        O.halo_exchange(ocs, P.F_GRADU)
+        O.exchange_cell_centres(ocs)
+        phis = [np.random.default_rng(23 + r).normal(size=c.mesh.nFaces) * 1e-6 for r, c in enumerate(parts)]
+        for ctx, phi in zip(ctxs, phis):
+            ctx.face_field_upload(P.FF_PHI, phi)
+            ctx.alpha_compression_coeff(0.9, 0.2, 0.5)
+        for ctx in ctxs:
+            ctx.sync()
+        for r, (ctx, case, oc, phi) in enumerate(zip(ctxs, parts, ocs, phis)):
+            m = case.mesh
+            got = ctx.face_field(P.FF_PHIC, m.nInternalFaces, m.nBoundaryFaces)
+            ref = oc.alpha_compression_coeff(phi, 0.9, 0.2, 0.5)
+            assert np.array_equal(got, ref), f"rank {r}: {np.count_nonzero(got != ref)} faces of phic differ"
+            proc = np.concatenate([np.arange(m.patchStart[p], m.patchStart[p] + m.patchSize[p])
+                                   for p in range(m.nPatches) if m.patchKind[p] == 1])
+            assert np.abs(got[proc]).min() > 0
         print(f"{n_ranks} in-process ranks ({decomp}): worst rel err {worst:.2e}, "
               f"{[c.halo_bytes_per_update() for c in ctxs]} halo bytes per update")
     finally:

@@ -519,3 +519,36 @@ def test_rerun_is_bitwise_deterministic(ctx):
         else:
             for a, b in zip(first, snap):
                 assert np.array_equal(a, b, equal_nan=True), rep
+
+
+@pytest.mark.parametrize("name", ["cfg1_sheared_graded", "cfg2_fks_kelvin", "cfg3_poly"])
+@pytest.mark.parametrize("coeffs", [(1.0, 0.0, 0.0), (1.0, 0.25, 0.0), (0.7, 0.3, 0.6)], ids=["plain", "ic", "ic+sc"])
+def test_alpha_compression_coefficient(ctx, name, coeffs):
+    """multiRegionVoF/alphaEqn.H:58-87: phic = cAlpha|phi/magSf| with the optional isotropic (icAlpha) and
+    shear (scAlpha) compression terms; IEEE-only arithmetic in the reference's operator order -> bit-exact"""
+    case = small_cases()[name]()
+    m = case.mesh
+    ctx.load_case(case)
+    oc = oracle_case(case)
+    oc.set(P.F_U, *ctx.download(P.F_U))
+    cA, ic, sc = coeffs
+    phi = np.random.default_rng(17).normal(size=m.nFaces) * 1e-6
+    if sc > 0:
+        ctx.grad_u()
+        oc.grad_u()
+        gi, gb = ctx.download(P.F_GRADU)
+        assert np.array_equal(np.concatenate([gi, gb]), oc.field(P.F_GRADU), equal_nan=True)
+    ctx.face_field_upload(P.FF_PHI, phi)
+    ctx.alpha_compression_coeff(cA, ic, sc)
+    got = ctx.face_field(P.FF_PHIC, m.nInternalFaces, m.nBoundaryFaces)
+    ref = oc.alpha_compression_coeff(phi, cA, ic, sc)
+    assert np.array_equal(got, ref), f"{np.count_nonzero(got != ref)} of {got.size} faces differ"
+    assert np.all(got[m.nInternalFaces:] == 0.0) and np.abs(got[: m.nInternalFaces]).min() > 0
+
+
+def test_alpha_compression_coefficient_needs_its_inputs(ctx):
+    case = small_cases()["cfg2_fks_kelvin"]()
+    ctx.load_case(case)
+    with pytest.raises(capi.SsamError) as e:
+        ctx.alpha_compression_coeff(1.0, 0.0, 0.0)
+    assert "phi" in str(e.value)

@@ -169,3 +169,93 @@ def test_div_dev_rho_reff_explicit_analytic():
             assert np.allclose(r[inner], [-(2.0 / 3.0) * scale, 0.0, 0.0], rtol=1e-9, atol=1e-9 * scale)
         # boundary values: the adjacent cell's value
         assert np.array_equal(oc.boundary(P.F_DIVDEVRHOREFF), r[m.owner[m.nInternalFaces:]])
+
+
+# ---- alphaEqn.H:58-87: the interface-compression coefficient phic (OpenFOAM semantics restated, analytic pins) ----------
+def test_alpha_compression_coefficient_analytic():
+    """orthogonal hex, linear U = G x with a symmetric G: fvc::grad(U) is exact in interior cells, so on interior
+    faces between interior cells  phic = cAlpha|phi|/|Sf| (1 - ic) + cAlpha ic |U|_f + sc |delta . G|  in closed form;
+    non-coupled boundary faces are zero."""
+    import numpy as np
+
+    from oracle import pyoracle as O
+    from solidstateamfoam_b200 import mesh as M
+    from solidstateamfoam_b200 import params as P
+
+    n = 6
+    h = 0.1
+    m = M.hex_block(n, n, n, length=(n * h, n * h, n * h))
+    G = np.array([[0.3, 0.1, -0.2], [0.1, -0.5, 0.4], [-0.2, 0.4, 0.2]])  # symmetric, U_j = sum_i x_i G_ij
+    X = np.concatenate([m.C, m.Cf[m.nInternalFaces:]])
+    U = X @ G
+    oc = O.OracleCase(m)
+    oc.set(P.F_U, U[: m.nCells], U[m.nCells:])
+    oc.grad_u()
+    rng = np.random.default_rng(3)
+    phi = rng.normal(size=m.nFaces) * h * h
+    cA, ic, sc = 1.0, 0.25, 0.5
+    phic = oc.alpha_compression_coeff(phi, cA, ic, sc)
+    assert np.all(phic[m.nInternalFaces:] == 0.0)
+    # interior cells: no boundary face
+    touches = np.zeros(m.nCells, dtype=bool)
+    touches[m.owner[m.nInternalFaces:]] = True
+    own, nei = m.owner[: m.nInternalFaces], m.neighbour
+    inner = ~touches[own] & ~touches[nei]
+    assert inner.sum() > 50
+    magSf = np.linalg.norm(m.Sf[: m.nInternalFaces], axis=1)
+    magU = np.linalg.norm(U[: m.nCells], axis=1)
+    magUf = 0.5 * (magU[own] + magU[nei])
+    delta = m.C[nei] - m.C[own]
+    expect = cA * np.abs(phi[: m.nInternalFaces]) / magSf * (1 - ic) + cA * ic * magUf + sc * np.linalg.norm(delta @ G, axis=1)
+    assert np.allclose(phic[: m.nInternalFaces][inner], expect[inner], rtol=1e-12, atol=0)
+    # the plain coefficient (icAlpha = scAlpha = 0) needs neither U nor gradU
+    oc2 = O.OracleCase(m)
+    p0 = oc2.alpha_compression_coeff(phi, 1.5, 0.0, 0.0)
+    assert np.allclose(p0[: m.nInternalFaces], 1.5 * np.abs(phi[: m.nInternalFaces]) / magSf, rtol=1e-15)
+
+
+def test_alpha_compression_coefficient_decomposed_equals_serial():
+    """processor faces: interpolation with the neighbour rank's values and mesh.delta() from the exchanged cell centres
+    reproduce the serial internal-face value (weights 0.5 on this uniform mesh: bit-identical interpolation)"""
+    import numpy as np
+
+    from oracle import pyoracle as O
+    from solidstateamfoam_b200 import mesh as M
+    from solidstateamfoam_b200 import params as P
+
+    n = 6
+    hblk = M.hex_block(n, n, n, _keep=True)
+    cp = (np.arange(n * n * n) // (n * n) >= n // 2).astype(np.int32)  # two z-slabs
+    g, parts = M.decompose(hblk, cp, 2)
+    rng = np.random.default_rng(5)
+    Xg = np.concatenate([g.C, g.Cf[g.nInternalFaces:]])
+    Ug = np.stack([np.sin(3 * Xg[:, 0]) + Xg[:, 2], np.cos(2 * Xg[:, 1]), Xg[:, 0] * Xg[:, 2]], axis=1)
+    phig = rng.normal(size=g.nFaces)
+    og = O.OracleCase(g)
+    og.set(P.F_U, Ug[: g.nCells], Ug[g.nCells:])
+    og.grad_u()
+    serial = og.alpha_compression_coeff(phig, 1.0, 0.3, 0.7)
+    ocs = []
+    for m in parts:
+        X = np.concatenate([m.C, m.Cf[m.nInternalFaces:]])
+        U = np.stack([np.sin(3 * X[:, 0]) + X[:, 2], np.cos(2 * X[:, 1]), X[:, 0] * X[:, 2]], axis=1)
+        oc = O.OracleCase(m)
+        oc.set(P.F_U, U[: m.nCells], U[m.nCells:])
+        ocs.append(oc)
+    O.halo_exchange(ocs, P.F_U)
+    for oc in ocs:
+        oc.grad_u()
+    O.halo_exchange(ocs, P.F_GRADU)
+    O.exchange_cell_centres(ocs)
+    for m, oc in zip(parts, ocs):
+        sign = np.where(m.faceFlip == 1, -1.0, 1.0)
+        phic = oc.alpha_compression_coeff(sign * phig[m.faceGlobal], 1.0, 0.3, 0.7)
+        for p in range(m.nPatches):
+            sl = slice(int(m.patchStart[p]), int(m.patchStart[p] + m.patchSize[p]))
+            if m.patchKind[p] == 1:  # processor faces = internal faces of the serial mesh
+                assert np.allclose(phic[sl], serial[m.faceGlobal[sl]], rtol=1e-12, atol=1e-15)
+                assert np.abs(phic[sl]).min() > 0
+            else:
+                assert np.all(phic[sl] == 0.0)
+        nif = m.nInternalFaces
+        assert np.allclose(phic[:nif], serial[m.faceGlobal[:nif]], rtol=1e-12, atol=1e-15)
