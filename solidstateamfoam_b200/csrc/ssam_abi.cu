@@ -67,6 +67,11 @@ struct ssam_ctx {
     std::vector<int> tileMaxCallerCell;  // per tile, for the host-staged pipeline (built on first use)
     std::vector<int> pipeWaitIn, pipeOutWait;  // chunk dependencies of that pipeline, cached per chunk count
     int pipeChunks = 0;
+    // launch order of the host-staged pipeline on a permuted layout: tiles sorted by their first caller cell, so that
+    // upload chunk -> compute chunk -> download chunk stay monotone whatever order the tiles have in memory
+    int* pipeList = nullptr;
+    int4* descPipe = nullptr;
+    std::vector<int> pipeListHost, pipePosOfTile;
     int *origOwner = nullptr, *origNeighbour = nullptr;  // the caller's owner / neighbour (permuted layout only)
     ssam_ctx* refAddr = nullptr;  // addressing tables in the caller's numbering, built on demand
     double remotePerCellCaller = 0.0, remotePerCellCompact = 0.0;
@@ -263,6 +268,10 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->invPerm);
     c->tileMaxCallerCell.clear();
     c->pipeChunks = 0;
+    devFree(c->pipeList);
+    devFree(c->descPipe);
+    c->pipeListHost.clear();
+    c->pipePosOfTile.clear();
     devFree(c->faceKey);
     devFree(c->origOwner);
     devFree(c->origNeighbour);
@@ -948,7 +957,7 @@ ssam_status launchCellsBoundary(ssam_ctx* ctx, const UpdateArgs& a, int model1, 
     return SSAM_OK;
 }
 
-template <int M, bool LIST>
+template <int M, bool LIST, bool FITS>
 ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, int count, cudaStream_t stream) {
     if (count == 0) return SSAM_OK;
     UpdateArgs a = a0;
@@ -961,6 +970,8 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
             a.tileDesc = ctx->descCoupled;
         } else if (list == ctx->tileOrder) {
             a.tileDesc = ctx->descOrder;
+        } else if (ctx->pipeList && list >= ctx->pipeList && list < ctx->pipeList + ctx->nTiles) {
+            a.tileDesc = ctx->descPipe + (list - ctx->pipeList);  // a range of the caller-order list
         } else {
             a.tileDesc = ctx->tileDesc + (list - ctx->tileIota);  // a range of the identity list
         }
@@ -968,10 +979,10 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
     static bool configured[64] = {false};  // per device: the attribute belongs to the device's context
     const int smem = int(sizeof(TileSmem));
     if (!configured[ctx->device & 63]) {
-        CU(cudaFuncSetAttribute(k_cells_tiled<M, LIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaFuncSetAttribute((k_cells_tiled<M, LIST, FITS>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured[ctx->device & 63] = true;
     }
-    k_cells_tiled<M, LIST><<<count, TILE, smem, stream>>>(a);
+    k_cells_tiled<M, LIST, FITS><<<count, TILE, smem, stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return SSAM_OK;
@@ -990,6 +1001,8 @@ ssam_status launchPipeOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, 
             a.tileDesc = ctx->descCoupled;
         } else if (list == ctx->tileOrder) {
             a.tileDesc = ctx->descOrder;
+        } else if (ctx->pipeList && list >= ctx->pipeList && list < ctx->pipeList + ctx->nTiles) {
+            a.tileDesc = ctx->descPipe + (list - ctx->pipeList);  // a range of the caller-order list
         } else {
             a.tileDesc = ctx->tileDesc + (list - ctx->tileIota);  // a range of the identity list
         }
@@ -1054,10 +1067,16 @@ ssam_status launchCellsPipe(ssam_ctx* ctx, const UpdateArgs& a, int model1, cons
 ssam_status launchCellsTiled(ssam_ctx* ctx, const UpdateArgs& a, int model1, const int* list, int count,
                              cudaStream_t stream) {
     if (ctx->cellKernel == 2) return launchCellsPipe(ctx, a, model1, list, count, stream);
-#define SSAM_TILED(M)                                                                   \
-    case M:                                                                             \
-        return list ? launchTiledOne<M, true>(ctx, a, list, count, stream)              \
-                    : launchTiledOne<M, false>(ctx, a, nullptr, count, stream);
+    // SSAM_FITS=0 keeps the general gather (with global-memory fallbacks) even when every tile fits (experiments)
+    static const bool allowFits = !(std::getenv("SSAM_FITS") && std::atoi(std::getenv("SSAM_FITS")) == 0);
+    const bool fits = allowFits && ctx->nTilesOversize == 0;
+#define SSAM_TILED(M)                                                                           \
+    case M:                                                                                     \
+        if (fits)                                                                               \
+            return list ? launchTiledOne<M, true, true>(ctx, a, list, count, stream)            \
+                        : launchTiledOne<M, false, true>(ctx, a, nullptr, count, stream);       \
+        return list ? launchTiledOne<M, true, false>(ctx, a, list, count, stream)               \
+                    : launchTiledOne<M, false, false>(ctx, a, nullptr, count, stream);
     switch (model1) {
         SSAM_TILED(SSAM_VISC_NEWTONIAN)
         SSAM_TILED(SSAM_VISC_SHEPPARD_WRIGHT)
@@ -2554,6 +2573,7 @@ struct ChunkPlan {
     int nChunks = 0, tilesPerChunk = 0;
     std::vector<cudaEvent_t> evIn, evOut;
     std::vector<int> waitIn;  // compute chunk k may start after upload chunk waitIn[k] (empty: k+1)
+    const int* list = nullptr;  // launch order of the tiles (device array of nTiles entries); nullptr = identity
 };
 
 static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, int flags,
@@ -2706,7 +2726,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
                 const int t0 = k * plan->tilesPerChunk, t1 = std::min(ctx->nTiles, t0 + plan->tilesPerChunk);
                 const int dep = plan->waitIn.empty() ? std::min(k + 1, plan->nChunks - 1) : plan->waitIn[size_t(k)];
                 CU(cudaStreamWaitEvent(ctx->stream, plan->evIn[size_t(dep)], 0));
-                TRY(launchCellsTiled(ctx, a, model1, ctx->tileIota + t0, t1 - t0, ctx->stream));
+                TRY(launchCellsTiled(ctx, a, model1, (plan->list ? plan->list : ctx->tileIota) + t0, t1 - t0, ctx->stream));
                 CU(cudaEventRecord(plan->evOut[k], ctx->stream));
             }
         } else if (ctx->cellKernel >= 1) {
@@ -2812,21 +2832,40 @@ static ssam_status updateFusedHostPipelined(ssam_ctx* ctx, const ssam_update_par
             CU(cudaStreamSynchronize(ctx->stream));
             cudaFree(d);
         }
+        if (ctx->pipeListHost.empty()) {
+            // tiles by their first (smallest) caller cell
+            const int nT = ctx->nTiles;
+            std::vector<int> first(size_t(nT), ctx->nCells);
+            for (int i = 0; i < ctx->nCells; ++i) first[size_t(i / TILE)] = std::min(first[size_t(i / TILE)], ctx->permHost[size_t(i)]);
+            ctx->pipeListHost.resize(size_t(nT));
+            for (int t = 0; t < nT; ++t) ctx->pipeListHost[size_t(t)] = t;
+            std::stable_sort(ctx->pipeListHost.begin(), ctx->pipeListHost.end(),
+                             [&](int x, int y) { return first[size_t(x)] < first[size_t(y)]; });
+            ctx->pipePosOfTile.resize(size_t(nT));
+            for (int q = 0; q < nT; ++q) ctx->pipePosOfTile[size_t(ctx->pipeListHost[size_t(q)])] = q;
+            TRY(devAlloc(ctx, &ctx->pipeList, size_t(nT)));
+            CU(cudaMemcpyAsync(ctx->pipeList, ctx->pipeListHost.data(), size_t(nT) * sizeof(int), cudaMemcpyHostToDevice,
+                               ctx->stream));
+            TRY(devAlloc(ctx, &ctx->descPipe, size_t(nT)));
+            LAUNCH(k_tile_desc_list, gridFor(nT, 256), 256, ctx->tileDesc, ctx->pipeList, nT, ctx->descPipe);
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
         if (ctx->pipeChunks != nChunks) {
             ctx->pipeWaitIn.assign(size_t(nChunks), nChunks - 1);
             for (int k = 0; k < nChunks; ++k) {
                 int m = 0;
-                for (int t = k * plan.tilesPerChunk; t < std::min(ctx->nTiles, (k + 1) * plan.tilesPerChunk); ++t)
-                    m = std::max(m, ctx->tileMaxCallerCell[size_t(t)]);
+                for (int q = k * plan.tilesPerChunk; q < std::min(ctx->nTiles, (k + 1) * plan.tilesPerChunk); ++q)
+                    m = std::max(m, ctx->tileMaxCallerCell[size_t(ctx->pipeListHost[size_t(q)])]);
                 ctx->pipeWaitIn[size_t(k)] = std::min(nChunks - 1, int(size_t(m) / chunkCells));
             }
             ctx->pipeOutWait.assign(size_t(nChunks), 0);
             for (int i = 0; i < ctx->nCells; ++i) {
                 const size_t j = size_t(ctx->permHost[size_t(i)]) / chunkCells;
-                ctx->pipeOutWait[j] = std::max(ctx->pipeOutWait[j], (i / TILE) / plan.tilesPerChunk);
+                ctx->pipeOutWait[j] = std::max(ctx->pipeOutWait[j], ctx->pipePosOfTile[size_t(i / TILE)] / plan.tilesPerChunk);
             }
             ctx->pipeChunks = nChunks;
         }
+        plan.list = ctx->pipeList;
         plan.waitIn = ctx->pipeWaitIn;
         outWait = ctx->pipeOutWait;
     }
@@ -2954,8 +2993,10 @@ ssam_status ssam_update_fused_host(ssam_ctx* ctx, const ssam_update_params* p, c
     // chunks of >= 1024 tiles, each at least as deep as the mesh bandwidth (so a chunk only gathers from
     // itself and its two neighbours)
     int nChunks = ctx->hostChunks >= 0 ? std::min(ctx->hostChunks, 64) : std::min(16, ctx->nTiles / 1024);
-    while (nChunks > 1 && (ctx->nTiles + nChunks - 1) / nChunks < ctx->bandwidthTiles + 1) --nChunks;
-    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel >= 1 && ctx->nTilesOversize == 0)
+    // caller-order layout: the chunk dependency is "the next chunk"; the permuted layout derives it from the mesh
+    if (!ctx->perm)
+        while (nChunks > 1 && (ctx->nTiles + nChunks - 1) / nChunks < ctx->bandwidthTiles + 1) --nChunks;
+    if (nChunks > 1 && ctx->nProcPatches == 0 && ctx->cellKernel >= 1)
         return updateFusedHostPipelined(ctx, p, io, nChunks);
     return updateFusedHostSimple(ctx, p, io);
 }
