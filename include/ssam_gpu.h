@@ -379,6 +379,10 @@ SSAM_API ssam_status ssam_interface_delta_n(ssam_ctx* ctx, double* deltaN);
  * itself (ssam_halo_exchange) MUST set it, otherwise the gradient reads stale halo values. */
 typedef enum { SSAM_FUSED_WRITE_GRAD = 1, SSAM_FUSED_HALO_INPUTS = 2 } ssam_fused_flags;
 SSAM_API ssam_status ssam_update_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags);
+/* Performs every allocation and lazy set-up ssam_update_fused(ctx, p, flags) would do (output planes, friction scratch,
+ * halo transport) without enqueuing an exchange.  Optional in one-process-per-GPU runs; required on every rank of an
+ * in-process rank group (ssam_comm_init_local) before its first collective update. */
+SSAM_API ssam_status ssam_prepare_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags);
 /* Host-staged drop-in of the same update: uploads U,T,alpha1,p (AoS host buffers, internal+boundary),
  * runs the fused kernels, downloads the listed output fields. Used for the e2e metric. */
 typedef struct ssam_host_io {

@@ -24,7 +24,7 @@ SYMBOLS = [
     "ssam_thermo_correct", "ssam_mixture_mu", "ssam_mixture_rho", "ssam_mixture_cp", "ssam_mixture_k", "ssam_mixture_k_phase",
     "ssam_solver_rho_rhocp", "ssam_stress_strain", "ssam_div_dev_rho_reff_explicit", "ssam_interface_correct",
     "ssam_interface_nhatf_download", "ssam_interface_nhatf_device_ptr", "ssam_interface_delta_n", "ssam_face_field_download", "ssam_face_field_upload", "ssam_alpha_compression_coeff",
-    "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused",
+    "ssam_face_field_device_ptr", "ssam_face_interpolate", "ssam_mixture_muf", "ssam_mixture_nuf", "ssam_field_min_max", "ssam_friction_correct", "ssam_friction_patch_centre", "ssam_update_fused", "ssam_prepare_fused",
     "ssam_update_fused_host", "ssam_set_host_chunks", "ssam_debug_math", "ssam_measure_fp64_peak", "ssam_comm_unique_id", "ssam_comm_init", "ssam_comm_init_local", "ssam_halo_exchange", "ssam_halo_transport", "ssam_halo_bytes_last_update",
 ]
 
@@ -104,6 +104,7 @@ def load():
     L.ssam_friction_correct.argtypes = [vp, C.POINTER(P.StickParams)]
     L.ssam_friction_patch_centre.argtypes = [vp, dp, dp]
     L.ssam_update_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
+    L.ssam_prepare_fused.argtypes = [vp, C.POINTER(P.UpdateParams), C.c_int]
     L.ssam_update_fused_host.argtypes = [vp, C.POINTER(P.UpdateParams), C.POINTER(P.HostIO)]
     L.ssam_set_host_chunks.argtypes = [vp, C.c_int]
     L.ssam_debug_math.argtypes = [vp, C.c_int, dp, dp, dp, C.c_int64]
@@ -356,6 +357,9 @@ class Context:
 
     def update_fused(self, p: P.UpdateParams, flags: int = 0):
         self._chk(self.L.ssam_update_fused(self.h, C.byref(p), flags))
+
+    def prepare_fused(self, p: P.UpdateParams, flags: int = 0):
+        self._chk(self.L.ssam_prepare_fused(self.h, C.byref(p), flags))
 
     def set_host_chunks(self, n: int):
         self._chk(self.L.ssam_set_host_chunks(self.h, n))

@@ -93,6 +93,7 @@ struct ssam_ctx {
     size_t stageCap = 0;
 
     int fricPatchCached = -1;
+    bool fusedPrepared = false;  // ssam_prepare_fused ran on this mesh (in-process rank groups require it)
     // boundary-face centres and areas as given by the caller: the friction-patch sums of an in-process rank group are
     // formed on the host (pure mesh geometry; no device synchronisation inside a collective update)
     std::vector<double> hostCfB, hostMagSfB;
@@ -303,6 +304,7 @@ void freeMesh(ssam_ctx* c) {
     devFree(c->cellFaces);
     devFree(c->faceColour);
     c->fricPatchCached = -1;
+    c->fusedPrepared = false;
     c->hostCfB.clear();
     c->hostMagSfB.clear();
     c->qfricZeroedFor = -2;
@@ -899,7 +901,9 @@ ssam_status ensureFricSums(ssam_ctx* ctx, int patch) {
             for (int k = 0; k < 4; ++k) tot[k] = r == 0 ? loc[k] : tot[k] + loc[k];
         }
         for (int k = 0; k < 4; ++k) ctx->fricHost[k] = tot[k];
-        CU(cudaMemcpyAsync(ctx->fricSums + 4, ctx->fricHost, 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        // by kernel argument: a pageable cudaMemcpyAsync would synchronise the stream, which may be parked on a wait
+        // for a rank whose work this host thread has not enqueued yet
+        LAUNCH(k_set4, 1, 1, ctx->fricSums + 4, tot[0], tot[1], tot[2], tot[3]);
     } else if (ctx->comm && ctx->nRanks > 1) {
         // reduce(patchCenter_, sumOp<vector>()); reduce(patchArea_, sumOp<scalar>())  (constantSlipStick.C:134-135)
         // NB every rank starts its area at VSMALL like the reference does.
@@ -2601,6 +2605,8 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         TRY(ensureField(ctx, SSAM_F_SIGMAY));
     }
     if (model1 == SSAM_VISC_NORTON_HOFF) TRY(ensureField(ctx, SSAM_F_STRAINRATE));
+    if (p->stick.fricPatch >= 0) TRY(ensureField(ctx, SSAM_F_QFRIC));
+    if (!ctx->fricSums) TRY(devAlloc(ctx, &ctx->fricSums, 8));
     if (flags & 1) {
         TRY(ensureField(ctx, SSAM_F_GRADU));
         for (int k = 0; k < 9; ++k) a.gradU[k] = ctx->plane[SSAM_F_GRADU][k];
@@ -2649,6 +2655,8 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     CHECK(ctx->nProcPatches == 0 || ctx->localPeers.empty() || !ctx->blocking, SSAM_ERR_INVALID,
           "in-process rank group: collective calls need ssam_set_blocking(ctx, 0) on every rank (enqueue all ranks, "
           "then synchronise)");
+    CHECK(ctx->nProcPatches == 0 || ctx->localPeers.empty() || ctx->fusedPrepared, SSAM_ERR_INVALID,
+          "in-process rank group: call ssam_prepare_fused on every rank before the first collective update");
     if (ctx->nProcPatches) TRY(ensureHaloTransport(ctx));
     const bool peer = split && ctx->p2p.state == 1;
     if (split && !peer && !ctx->commStream) {
@@ -2744,6 +2752,38 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     if (model1 == SSAM_VISC_NORTON_HOFF) ctx->isSet[SSAM_F_STRAINRATE] = true;
     if (flags & 1) ctx->isSet[SSAM_F_GRADU] = true;
     if (p->stick.fricPatch >= 0) TRY(launchQfric(ctx, p->stick));
+    return SSAM_OK;
+}
+
+// Everything an update allocates or sets up lazily, without enqueuing any exchange: fields, the friction scratch, the
+// halo transport.  Optional for one-process-per-GPU runs; REQUIRED before the first collective call of an in-process
+// rank group, where a host-blocking operation (allocation, pageable copy, lazy module load) issued while this rank's
+// stream is parked on a wait for a rank that the same host thread has not enqueued yet would deadlock.
+ssam_status ssam_prepare_fused(ssam_ctx* ctx, const ssam_update_params* p, int flags) {
+    if (ctx) cudaSetDevice(ctx->device);
+    CHECK(ctx && p && ctx->haveMesh, SSAM_ERR_INVALID, "mesh not set / null params");
+    const int model1 = p->visc1.model;
+    const int outs[] = {SSAM_F_EPSDOT, SSAM_F_NU1, SSAM_F_NU2, SSAM_F_NU,  SSAM_F_MUEFF, SSAM_F_RHO,
+                        SSAM_F_CP,     SSAM_F_K,   SSAM_F_QVISC, SSAM_F_SIGMAF, SSAM_F_SIGMAY};
+    for (int f : outs) TRY(ensureField(ctx, f));
+    if (model1 == SSAM_VISC_NORTON_HOFF) TRY(ensureField(ctx, SSAM_F_STRAINRATE));
+    if (flags & 1) TRY(ensureField(ctx, SSAM_F_GRADU));
+    if (p->stick.fricPatch >= 0) TRY(ensureField(ctx, SSAM_F_QFRIC));
+    if (!ctx->fricSums) TRY(devAlloc(ctx, &ctx->fricSums, 8));
+    if (ctx->cellKernel == 2 && !ctx->pipeSched) {
+        TRY(devAlloc(ctx, &ctx->pipeSched, 16));
+        CU(cudaMemsetAsync(ctx->pipeSched, 0, 16 * sizeof(int), ctx->stream));
+    }
+    for (int k = 0; k < 3 && ctx->nProcPatches; ++k)
+        if (!ctx->procNbrC[k]) {
+            TRY(devAlloc(ctx, &ctx->procNbrC[k], size_t(ctx->nBnd)));
+            CU(cudaMemsetAsync(ctx->procNbrC[k], 0, size_t(ctx->nBnd) * sizeof(double), ctx->stream));
+        }
+    TRY(ensureFaceField(ctx, SSAM_FF_PHI));
+    TRY(ensureFaceField(ctx, SSAM_FF_PHIC));
+    if (ctx->nProcPatches) TRY(ensureHaloTransport(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->fusedPrepared = true;
     return SSAM_OK;
 }
 

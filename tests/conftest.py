@@ -1,6 +1,11 @@
 import os
 import sys
 
+# In-process rank groups (tests/test_gpu_local_ranks.py) must never block the host while one rank's stream is parked on a
+# wait for another rank: load every kernel when its module is loaded instead of at first launch (a lazy load can
+# synchronise the device).  Must be set before CUDA is initialised, i.e. before anything below touches libcuda.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
