@@ -36,8 +36,8 @@ using namespace Foam;
 void stageViscosities(const ssamGpuMesh& gpu, const volScalarField& alpha1, const viscosityModel& m1, const viscosityModel& m2)
 {
     gpu.upload(SSAM_F_ALPHA1, alpha1);
-    gpu.upload(SSAM_F_NU1, m1.nu()());
-    gpu.upload(SSAM_F_NU2, m2.nu()());
+    ssamStageViscosity(gpu, 1, m1);
+    ssamStageViscosity(gpu, 2, m2);
 }
 
 tmp<volScalarField> fetch(const ssamGpuMesh& gpu, int field, const word& name, const volScalarField& like)

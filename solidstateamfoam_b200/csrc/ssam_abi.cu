@@ -125,6 +125,7 @@ struct ssam_ctx {
         void* peerMap[32] = {nullptr};      // IPC mappings this context opened (one per neighbour rank)
         double* peerBase[32] = {nullptr};   // per processor patch: the neighbour's receive buffer
         int peerOff[32] = {0};
+        size_t peerSlotDoubles[32] = {0};   // ... and the size of one of ITS two slots (ranks differ in processor faces)
         unsigned long long seq = 0;
     } p2p;
 
@@ -574,7 +575,9 @@ ssam_status p2pSetup(ssam_ctx* ctx) {
     const int nP = ctx->nProcPatches;
     struct Msg {
         cudaIpcMemHandle_t handle;
-        int off, size, pad[14];
+        int off, size;
+        long long slotDoubles;  // size of one receive slot of the sender of this message
+        int pad[12];
     };
     static_assert(sizeof(Msg) == 128, "handshake message size");
     std::vector<Msg> mine(static_cast<size_t>(nP)), theirs(static_cast<size_t>(nP));
@@ -596,6 +599,7 @@ ssam_status p2pSetup(ssam_ctx* ctx) {
         mine[size_t(p)].handle = h;
         mine[size_t(p)].off = ctx->haloOffsets[size_t(p)];
         mine[size_t(p)].size = ctx->haloOffsets[size_t(p) + 1] - ctx->haloOffsets[size_t(p)];
+        mine[size_t(p)].slotDoubles = (long long)P.slotDoubles;
     }
     TRY(devAlloc(ctx, &P.patchB0, size_t(nP) + 1));
     CU(cudaMemcpyAsync(P.patchB0, b0.data(), (size_t(nP) + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -633,6 +637,7 @@ ssam_status p2pSetup(ssam_ctx* ctx) {
         }
         P.peerBase[p] = static_cast<double*>(base);
         P.peerOff[p] = theirs[size_t(p)].off;
+        P.peerSlotDoubles[p] = size_t(theirs[size_t(p)].slotDoubles);
     }
     if (ctx->nRanks > 32) ok = 0;  // one flag word per neighbour rank, 32 words
     // every rank must take the same path
@@ -663,7 +668,7 @@ ssam_status haloPushPeer(ssam_ctx* ctx, const PlanePtrs& pl, int nc, cudaStream_
     for (int p = 0; p <= ctx->nProcPatches; ++p) L.offsets[p] = ctx->haloOffsets[size_t(p)];
     for (int p = 0; p < ctx->nProcPatches; ++p) {
         double* base = P.peerBase[p];
-        L.dst[p] = base + 32 + slot * P.slotDoubles;
+        L.dst[p] = base + 32 + slot * P.peerSlotDoubles[p];  // the RECEIVER's slot size, not this rank's
         L.dstOff[p] = P.peerOff[p];
         // the neighbour's flag word for this rank: indexed by this rank's number modulo 32
         L.flag[p] = reinterpret_cast<unsigned long long*>(base) + (ctx->rank & 31);
@@ -757,6 +762,7 @@ ssam_status p2pSetupLocal(ssam_ctx* ctx) {
         }
         P.peerBase[p] = nb->p2p.recvBuf;
         P.peerOff[p] = nb->haloOffsets[size_t(pq)];
+        P.peerSlotDoubles[p] = nb->p2p.slotDoubles;
     }
     CU(cudaSetDevice(ctx->device));
     P.state = 1;
