@@ -298,6 +298,10 @@ void freeMesh(ssam_ctx* c) {
         c->isSet[f] = false;
     }
     p2pFree(c);
+    // in-process rank group: the neighbours' links into this context's (now freed) receive slots are re-made at their
+    // next exchange
+    for (ssam_ctx* q : c->localPeers)
+        if (q != c) q->p2p.state = 0;
     devFree(c->haloSendCells);
     devFree(c->sendBuf);
     c->sendCap = 0;
@@ -974,10 +978,10 @@ ssam_status launchTiledOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list,
     a.tileList = list;
     a.tileCount = count;
     if (LIST) {
-        if (list == ctx->tileListInterior) {
-            a.tileDesc = ctx->descInterior;
-        } else if (list == ctx->tileListCoupled) {
-            a.tileDesc = ctx->descCoupled;
+        if (ctx->tileListInterior && list >= ctx->tileListInterior && list < ctx->tileListInterior + ctx->nTilesInterior) {
+            a.tileDesc = ctx->descInterior + (list - ctx->tileListInterior);
+        } else if (ctx->tileListCoupled && list >= ctx->tileListCoupled && list < ctx->tileListCoupled + ctx->nTilesCoupled) {
+            a.tileDesc = ctx->descCoupled + (list - ctx->tileListCoupled);
         } else if (list == ctx->tileOrder) {
             a.tileDesc = ctx->descOrder;
         } else if (ctx->pipeList && list >= ctx->pipeList && list < ctx->pipeList + ctx->nTiles) {
@@ -1005,10 +1009,10 @@ ssam_status launchPipeOne(ssam_ctx* ctx, const UpdateArgs& a0, const int* list, 
     a.tileList = list;
     a.tileCount = count;
     if (list) {
-        if (list == ctx->tileListInterior) {
-            a.tileDesc = ctx->descInterior;
-        } else if (list == ctx->tileListCoupled) {
-            a.tileDesc = ctx->descCoupled;
+        if (ctx->tileListInterior && list >= ctx->tileListInterior && list < ctx->tileListInterior + ctx->nTilesInterior) {
+            a.tileDesc = ctx->descInterior + (list - ctx->tileListInterior);
+        } else if (ctx->tileListCoupled && list >= ctx->tileListCoupled && list < ctx->tileListCoupled + ctx->nTilesCoupled) {
+            a.tileDesc = ctx->descCoupled + (list - ctx->tileListCoupled);
         } else if (list == ctx->tileOrder) {
             a.tileDesc = ctx->descOrder;
         } else if (ctx->pipeList && list >= ctx->pipeList && list < ctx->pipeList + ctx->nTiles) {
@@ -1554,6 +1558,19 @@ ssam_status ssam_destroy(ssam_ctx* ctx) {
     if (!ctx) return SSAM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    // an in-process rank group ends with its first member: the others must not push into this context's freed slots
+    for (ssam_ctx* q : ctx->localPeers) {
+        if (q == ctx) continue;
+        cudaSetDevice(q->device);
+        cudaStreamSynchronize(q->stream);
+        p2pFree(q);
+        q->localPeers.clear();
+        q->rank = 0;
+        q->nRanks = 1;
+        q->fricPatchCached = -1;
+    }
+    ctx->localPeers.clear();
+    cudaSetDevice(ctx->device);
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     freeMesh(ctx);
     devFree(ctx->stage);
@@ -2648,8 +2665,8 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     // Multi-GPU schedules (tiled kernels).  The tiles are split into "interior" ones and "coupled" ones (a
     // cell of the tile has a processor face, so its gradient needs the neighbour rank's U).
     //  (a) peer memory (default), everything on ONE stream:
-    //        push(U,temp,alpha1) -> interior tiles -> wait flags + unpack -> coupled tiles -> push(epsilonDotEq[,..])
-    //        -> wait flags + unpack -> boundary faces
+    //        push(U,temp,alpha1) -> interior tiles (1st half) -> wait flags + unpack -> coupled tiles
+    //        -> push(epsilonDotEq[,..]) -> interior tiles (2nd half) -> wait flags + unpack -> boundary faces
     //      push = one small kernel storing straight into the neighbours' IPC-mapped receive slots over NVLink and
     //      publishing a flag; wait = a stream memory operation.  The neighbours' values travel while the interior
     //      tiles (75-99 % of the step) run, no library kernel shares the SMs with them, and a rank blocks only when
@@ -2696,13 +2713,14 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         ctx->profEvents.emplace_back(e0, e1);
         return SSAM_OK;
     };
-    auto launchInterior = [&]() -> ssam_status {
+    auto launchInterior = [&](int first, int count) -> ssam_status {  // interior tiles [first, first + count)
+        if (count <= 0) return SSAM_OK;
         if (ctx->interiorRange0 >= 0) {
             UpdateArgs ar = a;
-            ar.tileOffset = ctx->interiorRange0;
-            return launchCellsTiled(ctx, ar, model1, nullptr, ctx->nTilesInterior, ctx->stream);
+            ar.tileOffset = ctx->interiorRange0 + first;
+            return launchCellsTiled(ctx, ar, model1, nullptr, count, ctx->stream);
         }
-        return launchCellsTiled(ctx, a, model1, ctx->tileListInterior, ctx->nTilesInterior, ctx->stream);
+        return launchCellsTiled(ctx, a, model1, ctx->tileListInterior + first, count, ctx->stream);
     };
     cudaEvent_t pe = nullptr;
     if (peer) {
@@ -2711,22 +2729,28 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         TRY(planesOf(ctx, ins, 3, plIn, ncIn));
         TRY(planesOf(ctx, outs2, n2, plOut, ncOut));
         unsigned long long seqIn = 0, seqOut = 0;
+        // both exchanges travel behind interior work: the inputs behind the first part of the interior tiles, the
+        // outputs (epsilonDotEq of the processor-adjacent cells) behind the second
+        const int nA = ctx->nTilesInterior / 2, nB = ctx->nTilesInterior - nA;
         if (haloInputs) TRY(haloPushPeer(ctx, plIn, ncIn, ctx->stream, &seqIn));
         TRY(profBegin(pe));
-        TRY(launchInterior());
+        TRY(launchInterior(0, nA));
         TRY(profEnd(pe));
         if (haloInputs) TRY(haloWaitUnpackPeer(ctx, plIn, ncIn, seqIn, ctx->stream));
         TRY(profBegin(pe));
         TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->stream));
         TRY(profEnd(pe));
         TRY(haloPushPeer(ctx, plOut, ncOut, ctx->stream, &seqOut));
+        TRY(profBegin(pe));
+        TRY(launchInterior(nA, nB));
+        TRY(profEnd(pe));
         TRY(haloWaitUnpackPeer(ctx, plOut, ncOut, seqOut, ctx->stream));
     } else if (split) {
         TRY(profBegin(pe));
         CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->commStream, ctx->evMainToComm, 0));
         if (haloInputs) TRY(haloExchangeFields(ctx, ins, 3, ctx->commStream));
-        TRY(launchInterior());
+        TRY(launchInterior(0, ctx->nTilesInterior));
         TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->commStream));
         TRY(haloExchangeFields(ctx, outs2, n2, ctx->commStream));
         CU(cudaEventRecord(ctx->evCommToMain, ctx->commStream));
