@@ -45,6 +45,7 @@ struct ssam_ctx {
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     cudaStream_t commStream = nullptr;
     cudaEvent_t evMainToComm = nullptr, evCommToMain = nullptr;
+    cudaEvent_t evHaloIn = nullptr, evCoupledDone = nullptr;  // peer schedule: inputs unpacked / coupled tiles finished
     int pfDist = 148;    // L2 prefetch distance of the tiled kernel, in tiles (measured optimum, profiles/)
     int bandwidthTiles = 0;  // ceil(max(neighbour - owner) / TILE)
     // 97th percentile of the tile distance of the internal faces: where the HEAVY forward neighbours sit (a tile order
@@ -1580,6 +1581,8 @@ ssam_status ssam_destroy(ssam_ctx* ctx) {
     if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
     if (ctx->evMainToComm) cudaEventDestroy(ctx->evMainToComm);
     if (ctx->evCommToMain) cudaEventDestroy(ctx->evCommToMain);
+    if (ctx->evHaloIn) cudaEventDestroy(ctx->evHaloIn);
+    if (ctx->evCoupledDone) cudaEventDestroy(ctx->evCoupledDone);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     delete ctx;
     return SSAM_OK;
@@ -2593,6 +2596,21 @@ ssam_status ssam_friction_patch_centre(ssam_ctx* ctx, double centre[3], double* 
     return SSAM_OK;
 }
 
+// the high-priority side stream of the multi-rank schedules and the events that tie it to the main stream
+static ssam_status ensureSideStream(ssam_ctx* ctx) {
+    if (ctx->commStream) return SSAM_OK;
+    // highest priority: the side stream's small kernels must get SM slots as soon as CTAs of the
+    // interior-tile kernel retire, not after its whole grid has been dispatched
+    int prLo = 0, prHi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+    CU(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, prHi));
+    CU(cudaEventCreateWithFlags(&ctx->evMainToComm, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evCommToMain, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evHaloIn, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evCoupledDone, cudaEventDisableTiming));
+    return SSAM_OK;
+}
+
 // ---- fused update ---------------------------------------------------------------------------------------------
 // Host-staged pipeline (ssam_update_fused_host): the cell kernel runs chunk by chunk (contiguous tile
 // ranges); chunk k starts when the inputs of chunks <= k+1 have landed and signals evOut[k] when done.
@@ -2682,15 +2700,7 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
           "in-process rank group: call ssam_prepare_fused on every rank before the first collective update");
     if (ctx->nProcPatches) TRY(ensureHaloTransport(ctx));
     const bool peer = split && ctx->p2p.state == 1;
-    if (split && !peer && !ctx->commStream) {
-        // highest priority: the comm stream's small kernels must get SM slots as soon as CTAs of the
-        // interior-tile kernel retire, not after its whole grid has been dispatched
-        int prLo = 0, prHi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
-        CU(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, prHi));
-        CU(cudaEventCreateWithFlags(&ctx->evMainToComm, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&ctx->evCommToMain, cudaEventDisableTiming));
-    }
+    if (split) TRY(ensureSideStream(ctx));
     int outs2[3], n2 = 0;
     outs2[n2++] = SSAM_F_EPSDOT;
     if (model1 == SSAM_VISC_NORTON_HOFF) outs2[n2++] = SSAM_F_STRAINRATE;
@@ -2729,22 +2739,36 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         TRY(planesOf(ctx, ins, 3, plIn, ncIn));
         TRY(planesOf(ctx, outs2, n2, plOut, ncOut));
         unsigned long long seqIn = 0, seqOut = 0;
-        // both exchanges travel behind interior work: the inputs behind the first part of the interior tiles, the
-        // outputs (epsilonDotEq of the processor-adjacent cells) behind the second
+        // The small push / wait / unpack pieces run on the high-priority side stream beside the interior tiles (they
+        // are a few microseconds of kernel each and never spin, unlike an NCCL send/recv kernel); the main stream only
+        // meets them where it must: coupled tiles after the inputs are unpacked, boundary faces after the outputs are.
+        //   main: interior (1st half) ....... | coupled tiles | interior (2nd half) ............ | boundary faces
+        //   side: push(in) wait unpack -------^               ^--- push(out) wait unpack -------^
         const int nA = ctx->nTilesInterior / 2, nB = ctx->nTilesInterior - nA;
-        if (haloInputs) TRY(haloPushPeer(ctx, plIn, ncIn, ctx->stream, &seqIn));
+        cudaStream_t side = ctx->commStream;
+        CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
+        CU(cudaStreamWaitEvent(side, ctx->evMainToComm, 0));
+        if (haloInputs) {
+            TRY(haloPushPeer(ctx, plIn, ncIn, side, &seqIn));
+            TRY(haloWaitUnpackPeer(ctx, plIn, ncIn, seqIn, side));
+        }
+        CU(cudaEventRecord(ctx->evHaloIn, side));
         TRY(profBegin(pe));
         TRY(launchInterior(0, nA));
         TRY(profEnd(pe));
-        if (haloInputs) TRY(haloWaitUnpackPeer(ctx, plIn, ncIn, seqIn, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evHaloIn, 0));
         TRY(profBegin(pe));
         TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->stream));
         TRY(profEnd(pe));
-        TRY(haloPushPeer(ctx, plOut, ncOut, ctx->stream, &seqOut));
+        CU(cudaEventRecord(ctx->evCoupledDone, ctx->stream));
+        CU(cudaStreamWaitEvent(side, ctx->evCoupledDone, 0));
+        TRY(haloPushPeer(ctx, plOut, ncOut, side, &seqOut));
+        TRY(haloWaitUnpackPeer(ctx, plOut, ncOut, seqOut, side));
+        CU(cudaEventRecord(ctx->evCommToMain, side));
         TRY(profBegin(pe));
         TRY(launchInterior(nA, nB));
         TRY(profEnd(pe));
-        TRY(haloWaitUnpackPeer(ctx, plOut, ncOut, seqOut, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->evCommToMain, 0));
     } else if (split) {
         TRY(profBegin(pe));
         CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
@@ -2811,7 +2835,10 @@ ssam_status ssam_prepare_fused(ssam_ctx* ctx, const ssam_update_params* p, int f
         }
     TRY(ensureFaceField(ctx, SSAM_FF_PHI));
     TRY(ensureFaceField(ctx, SSAM_FF_PHIC));
-    if (ctx->nProcPatches) TRY(ensureHaloTransport(ctx));
+    if (ctx->nProcPatches) {
+        TRY(ensureHaloTransport(ctx));
+        TRY(ensureSideStream(ctx));
+    }
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->fusedPrepared = true;
     return SSAM_OK;
