@@ -56,6 +56,8 @@ def main():
             if s.startswith("stall_") and "Not Issued" not in s:
                 stalls[s] += int(r[ix[s]] or 0)
     print("per-cell instruction mix:", ", ".join(f"{op} {n * 32 / ncells:.0f}" for op, n in byop.most_common(22)))
+    fp64 = sum(n for op, n in byop.items() if op in ("DADD", "DMUL", "DFMA", "DSETP", "DMNMX")) * 32 / ncells
+    print(f"FP64 thread-instructions per cell (DADD+DMUL+DFMA+DSETP+DMNMX): {fp64:.1f}")
     print("stall samples:", ", ".join(f"{k[6:]} {v}" for k, v in stalls.most_common(8)))
 
 

@@ -2683,8 +2683,8 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
     // Multi-GPU schedules (tiled kernels).  The tiles are split into "interior" ones and "coupled" ones (a
     // cell of the tile has a processor face, so its gradient needs the neighbour rank's U).
     //  (a) peer memory (default), everything on ONE stream:
-    //        push(U,temp,alpha1) -> interior tiles (1st half) -> wait flags + unpack -> coupled tiles
-    //        -> push(epsilonDotEq[,..]) -> interior tiles (2nd half) -> wait flags + unpack -> boundary faces
+    //        side stream: push(U,temp,alpha1) -> wait flags + unpack -> coupled tiles -> push(epsilonDotEq[,..])
+    //        -> wait flags + unpack; main stream: all interior tiles, then (after the side stream) the boundary faces
     //      push = one small kernel storing straight into the neighbours' IPC-mapped receive slots over NVLink and
     //      publishing a flag; wait = a stream memory operation.  The neighbours' values travel while the interior
     //      tiles (75-99 % of the step) run, no library kernel shares the SMs with them, and a rank blocks only when
@@ -2739,12 +2739,14 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
         TRY(planesOf(ctx, ins, 3, plIn, ncIn));
         TRY(planesOf(ctx, outs2, n2, plOut, ncOut));
         unsigned long long seqIn = 0, seqOut = 0;
-        // The small push / wait / unpack pieces run on the high-priority side stream beside the interior tiles (they
-        // are a few microseconds of kernel each and never spin, unlike an NCCL send/recv kernel); the main stream only
-        // meets them where it must: coupled tiles after the inputs are unpacked, boundary faces after the outputs are.
-        //   main: interior (1st half) ....... | coupled tiles | interior (2nd half) ............ | boundary faces
-        //   side: push(in) wait unpack -------^               ^--- push(out) wait unpack -------^
-        const int nA = ctx->nTilesInterior / 2, nB = ctx->nTilesInterior - nA;
+        // Everything that depends on another rank runs on the high-priority side stream beside ONE launch of all
+        // interior tiles: push, stream-ordered wait and unpack of the inputs, the coupled tiles, push / wait / unpack of
+        // the outputs.  None of these pieces ever spins (an NCCL send/recv kernel does), the small kernels get SM slots
+        // as interior CTAs retire, and the main stream has no launch boundary inside the step:
+        //   main: interior tiles ............................................................ | boundary faces
+        //   side: push(in) wait unpack | coupled tiles | push(out) wait unpack ---------------^
+        // (Measured at 2 GPUs on the 64M-cell box, profiles/r2_scaling.md: splitting the interior launch in two around
+        // the coupled tiles on one stream costs ~60 us of launch-boundary bubbles per step.)
         cudaStream_t side = ctx->commStream;
         CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
         CU(cudaStreamWaitEvent(side, ctx->evMainToComm, 0));
@@ -2752,23 +2754,14 @@ static ssam_status updateFusedAsync(ssam_ctx* ctx, const ssam_update_params* p, 
             TRY(haloPushPeer(ctx, plIn, ncIn, side, &seqIn));
             TRY(haloWaitUnpackPeer(ctx, plIn, ncIn, seqIn, side));
         }
-        CU(cudaEventRecord(ctx->evHaloIn, side));
         TRY(profBegin(pe));
-        TRY(launchInterior(0, nA));
-        TRY(profEnd(pe));
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->evHaloIn, 0));
-        TRY(profBegin(pe));
-        TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, ctx->stream));
-        TRY(profEnd(pe));
-        CU(cudaEventRecord(ctx->evCoupledDone, ctx->stream));
-        CU(cudaStreamWaitEvent(side, ctx->evCoupledDone, 0));
+        TRY(launchInterior(0, ctx->nTilesInterior));
+        TRY(launchCellsTiled(ctx, a, model1, ctx->tileListCoupled, ctx->nTilesCoupled, side));
         TRY(haloPushPeer(ctx, plOut, ncOut, side, &seqOut));
         TRY(haloWaitUnpackPeer(ctx, plOut, ncOut, seqOut, side));
         CU(cudaEventRecord(ctx->evCommToMain, side));
-        TRY(profBegin(pe));
-        TRY(launchInterior(nA, nB));
-        TRY(profEnd(pe));
         CU(cudaStreamWaitEvent(ctx->stream, ctx->evCommToMain, 0));
+        TRY(profEnd(pe));
     } else if (split) {
         TRY(profBegin(pe));
         CU(cudaEventRecord(ctx->evMainToComm, ctx->stream));
