@@ -59,7 +59,7 @@ def build_cuda(force: bool = False, verbose: bool = False, extra: list[str] | No
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, "libssam_gpu.so")
     cu = _walk(CSRC, (".cu",))
-    deps = cu + _walk(CSRC, (".cuh", ".h")) + _walk(os.path.join(ROOT, "include"), (".h",))
+    deps = cu + _walk(CSRC, (".cuh", ".h", ".inc")) + _walk(os.path.join(ROOT, "include"), (".h",))
     if not force and _newer(target, deps):
         return target
     cmd = [nvcc_path(), *NVCC_ARCH, "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
