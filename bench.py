@@ -471,53 +471,66 @@ def run_gpu(args):
     sustained = total_cells * n_extra / (ms_sus * 1e-3) / 1e6
 
     # ---- e2e: host buffers through ssam_update_fused_host, same context / same cell layout ---------------
-    def pinned(a):
-        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+    def e2e_leg():
+        def pinned(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
 
-    gi, gb = ctx.download(P.F_U)  # U with the tool-patch BC applied, as the solver would hold it
+        gi, gb = ctx.download(P.F_U)  # U with the tool-patch BC applied, as the solver would hold it
+        ins = {"U_i": pinned(gi), "U_b": pinned(gb), "T_i": pinned(case.T_i), "T_b": pinned(case.T_b),
+               "alpha1_i": pinned(case.alpha1_i), "alpha1_b": pinned(case.alpha1_b), "p_i": pinned(case.p_i),
+               "p_b": pinned(case.p_b)}
+        del gi, gb
+        outs = [getattr(P, "F_" + n) for n in SOLVER_CONSUMED]
+        ref_out_i, _ = ctx.download(outs[0])
+        nOut = len(outs)
+        out_i = [torch.empty(mesh.nCells, dtype=torch.float64).pin_memory() for _ in outs]
+        out_b = [torch.empty(max(mesh.nBoundaryFaces, 1), dtype=torch.float64).pin_memory() for _ in outs]
+        dp = C.POINTER(C.c_double)
+        io = P.HostIO()
+        for k, v in ins.items():
+            setattr(io, k, C.cast(v.data_ptr(), dp))
+        io.nOut = nOut
+        of = (C.c_int32 * nOut)(*outs)
+        oi = (dp * nOut)(*[C.cast(x.data_ptr(), dp) for x in out_i])
+        ob = (dp * nOut)(*[C.cast(x.data_ptr(), dp) for x in out_b])
+        io.outFields, io.out_i, io.out_b = of, oi, ob
+        h2d = sum(v.numel() * 8 for v in ins.values())
+        d2h = nOut * (mesh.nCells + mesh.nBoundaryFaces) * 8
+        e2e_steps = max(2, min(args.steps, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            ctx.update_fused_host(case.params, io)
+        barrier()
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            ctx.update_fused_host(case.params, io)
+        e1.record(stream)
+        barrier()
+        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if n_ranks > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_value = total_cells * e2e_steps / (float(t2.item()) * 1e-3) / 1e6
+        # the e2e outputs must be the update's results, not stale buffers
+        assert np.array_equal(out_i[0].numpy(), ref_out_i, equal_nan=True), "e2e output mismatch"
+        del ref_out_i
+        return {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "outputs": list(SOLVER_CONSUMED), "cell_layout": layout_dev,
+                "note": "same context and cell layout as `value`; D2H = the fields the solver consumes per step "
+                        "(TEqn.H:3-15,25 and thermo.nu())"}
+
     layout_dev = "tile-compact" if ctx.layout_is_compact() else "caller order"
-    ins = {"U_i": pinned(gi), "U_b": pinned(gb), "T_i": pinned(case.T_i), "T_b": pinned(case.T_b),
-           "alpha1_i": pinned(case.alpha1_i), "alpha1_b": pinned(case.alpha1_b), "p_i": pinned(case.p_i),
-           "p_b": pinned(case.p_b)}
-    del gi, gb
-    outs = [getattr(P, "F_" + n) for n in SOLVER_CONSUMED]
-    ref_out_i, _ = ctx.download(outs[0])
-    nOut = len(outs)
-    out_i = [torch.empty(mesh.nCells, dtype=torch.float64).pin_memory() for _ in outs]
-    out_b = [torch.empty(max(mesh.nBoundaryFaces, 1), dtype=torch.float64).pin_memory() for _ in outs]
-    dp = C.POINTER(C.c_double)
-    io = P.HostIO()
-    for k, v in ins.items():
-        setattr(io, k, C.cast(v.data_ptr(), dp))
-    io.nOut = nOut
-    of = (C.c_int32 * nOut)(*outs)
-    oi = (dp * nOut)(*[C.cast(x.data_ptr(), dp) for x in out_i])
-    ob = (dp * nOut)(*[C.cast(x.data_ptr(), dp) for x in out_b])
-    io.outFields, io.out_i, io.out_b = of, oi, ob
-    h2d = sum(v.numel() * 8 for v in ins.values())
-    d2h = nOut * (mesh.nCells + mesh.nBoundaryFaces) * 8
-    e2e_steps = max(2, min(args.steps, 5))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(2):
-        ctx.update_fused_host(case.params, io)
-    barrier()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        ctx.update_fused_host(case.params, io)
-    e1.record(stream)
-    barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if n_ranks > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = total_cells * e2e_steps / (float(t2.item()) * 1e-3) / 1e6
-    # the e2e outputs must be the update's results, not stale buffers
-    assert np.array_equal(out_i[0].numpy(), ref_out_i, equal_nan=True), "e2e output mismatch"
-    del ref_out_i
+    try:
+        e2e = e2e_leg()
+    except Exception as exc:  # the device-resident line must still be printed; the failure is part of it
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "error": f"{type(exc).__name__}: {exc}"[:400]}
+        log(f"[rank {rank}] e2e leg failed: {exc}")
+        if n_ranks > 1:
+            raise  # a rank that left the collective sequence cannot be resynchronised
     fp64_peak = ctx.fp64_peak() if hasattr(ctx, "fp64_peak") else None
     transport = ctx.halo_transport()
     nvl = ctx.halo_bytes_per_update() if hasattr(ctx, "halo_bytes_per_update") else None
     ctx.close()
-    del ins, out_i, out_b, io
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -553,19 +566,23 @@ def run_gpu(args):
                           "ms_per_step": round(ms_sus / n_extra, 4)},
             "parity": parity,
             "roofline": roof,
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "outputs": list(SOLVER_CONSUMED), "cell_layout": layout_dev,
-                    "note": "same context and cell layout as `value`; D2H = the fields the solver consumes per step "
-                            "(TEqn.H:3-15,25 and thermo.nu())"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         if n_ranks == 1 and not args.no_extra:
-            line["extra_workloads"] = extra_workloads(args, stream, torch, peak)
+            try:
+                line["extra_workloads"] = extra_workloads(args, stream, torch, peak)
+            except Exception as exc:
+                line["extra_workloads"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
         if n_ranks == 1 and not args.no_cpu_baseline:
-            v, threads, sample, ms = cpu_arm(args.workload, 3, 1)
-            line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": sample}
+            try:
+                v, threads, sample, ms = cpu_arm(args.workload, 3, 1)
+                line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                                        "sample": sample}
+            except Exception as exc:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                        "sample": f"failed: {type(exc).__name__}: {exc}"[:400]}
         print(json.dumps(line), flush=True)
     if n_ranks > 1:
         dist.barrier()

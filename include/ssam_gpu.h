@@ -430,10 +430,11 @@ SSAM_API ssam_status ssam_comm_init_local(ssam_ctx** ctxs, int nRanks);
 /* Transport of the processor-patch exchanges: 1 = peer memory over NVLink (the pack kernel stores straight into the
  * neighbour's IPC-mapped receive slot and publishes a flag; the receiver waits with a stream memory operation),
  * 2 = grouped ncclSend/ncclRecv, 0 = not decided yet (before the first exchange) or no processor patches.
- * Default is peer memory: ssam_update_fused then runs push(U,temp,alpha1) -> interior tiles -> wait + unpack -> coupled
- * tiles -> push(epsilonDotEq) -> wait + unpack -> boundary faces on one stream, so the halos travel while the interior
- * tiles run and no library kernel shares the SMs with them.  SSAM_HALO=nccl in the environment selects the NCCL
- * exchange, which is also the fallback when a neighbour's memory cannot be mapped. */
+ * One process per GPU: NCCL by default; SSAM_HALO=p2p in the environment selects peer memory (falls back to NCCL when
+ * a neighbour's memory cannot be mapped).  In-process rank groups (ssam_comm_init_local) always use peer memory.
+ * Either way ssam_update_fused runs everything that depends on another rank -- exchange of U, temp, alpha1, the tiles
+ * that touch a processor patch, exchange of epsilonDotEq -- on a high-priority side stream beside one launch of all
+ * interior tiles. */
 SSAM_API int ssam_halo_transport(const ssam_ctx* ctx);
 /* Bytes this rank stored into its neighbours' memory (or sent through NCCL) during the last ssam_update_fused. */
 SSAM_API int64_t ssam_halo_bytes_last_update(const ssam_ctx* ctx);
