@@ -33,6 +33,7 @@ import os as _os
 _os.environ.setdefault("NCCL_MAX_NCHANNELS", "4")
 import argparse
 import ctypes as C
+import faulthandler
 import json
 import math
 import os
@@ -397,13 +398,24 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def phase(name, limit_s):
+        """one stderr line per phase, and a watchdog: a phase that exceeds its limit (a stalled collective) dumps every
+        thread's Python stack and ends the process instead of hanging the caller"""
+        if rank == 0 or os.environ.get("SSAM_BENCH_VERBOSE"):
+            log(f"[rank {rank}] phase: {name}")
+        faulthandler.cancel_dump_traceback_later()
+        if limit_s:
+            faulthandler.dump_traceback_later(limit_s, exit=True)
+
     # ---- parity first: nothing is timed unless the decomposed results match the oracle -------------------
     parity = None
+    phase("parity record", 600)
     if not args.no_parity:
         t0 = time.time()
         parity = parity_record(rank, n_ranks, local, dist, args.cell_kernel)
         log(f"[rank {rank}] parity ok ({parity['decomps']}, max rel {parity['max_rel']:.2e}) in {time.time() - t0:.1f}s")
 
+    phase("mesh generation + upload", 900)
     t0 = time.time()
     case = build_case(args.workload, rank, n_ranks, args.decomp)
     mesh = case.mesh
@@ -431,9 +443,11 @@ def run_gpu(args):
 
     # ---- device-resident timing ------------------------------------------------------------------
     sampler = ClockSampler(local)
+    phase("warm-up updates", 300)
     for _ in range(args.warmup):
         ctx.update_fused(case.params, flags)
     barrier()
+    phase("timed updates + sustained tail", 300)
     if rank == 0:
         sampler.start()
     ms_total, launches, cells_ms, cells_n = time_updates(ctx, case, flags, args.steps, 0, stream, barrier, torch)
@@ -519,6 +533,7 @@ def run_gpu(args):
                         "(TEqn.H:3-15,25 and thermo.nu())"}
 
     layout_dev = "tile-compact" if ctx.layout_is_compact() else "caller order"
+    phase("e2e leg (host buffers)", 600)
     try:
         e2e = e2e_leg()
     except Exception as exc:  # the device-resident line must still be printed; the failure is part of it
@@ -527,10 +542,13 @@ def run_gpu(args):
         log(f"[rank {rank}] e2e leg failed: {exc}")
         if n_ranks > 1:
             raise  # a rank that left the collective sequence cannot be resynchronised
+    phase("fp64 ceiling + teardown", 300)
     fp64_peak = ctx.fp64_peak() if hasattr(ctx, "fp64_peak") else None
     transport = ctx.halo_transport()
     nvl = ctx.halo_bytes_per_update() if hasattr(ctx, "halo_bytes_per_update") else None
+    barrier()  # no rank frees buffers a neighbour may still be using
     ctx.close()
+    phase("report", 1800 if n_ranks == 1 else 300)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -584,6 +602,7 @@ def run_gpu(args):
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                         "sample": f"failed: {type(exc).__name__}: {exc}"[:400]}
         print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if n_ranks > 1:
         dist.barrier()
         dist.destroy_process_group()

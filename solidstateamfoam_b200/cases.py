@@ -260,6 +260,19 @@ def block_grid(n_ranks: int, dims) -> tuple:
     return best[1]
 
 
+def _block_sides(idx, grid) -> tuple:
+    """neighbour rank across each of the six sides (xmin, xmax, ymin, ymax, zmin, zmax) of block idx of a structured
+    grid of blocks numbered x-fastest; -1 = physical boundary"""
+    side = [-1] * 6
+    for a in range(3):
+        for s, d in ((0, -1), (1, +1)):
+            j = list(idx)
+            j[a] += d
+            if 0 <= j[a] < grid[a]:
+                side[2 * a + s] = j[0] + grid[0] * (j[1] + grid[1] * j[2])
+    return tuple(side)
+
+
 def cfg5_part(rank: int, n_ranks: int, decomp: str = "block", dims=(512, 512, 256)) -> Case:
     """rank's partition of the cfg5 AFSD box (BASELINE.json configs[4]: 64M cells, SheppardWright), generated
     directly with its processor patches (no global mesh is ever built).  decomp = "block": structured blocks with up
@@ -272,18 +285,8 @@ def cfg5_part(rank: int, n_ranks: int, decomp: str = "block", dims=(512, 512, 25
     idx = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
     loc = tuple(dims[a] // grid[a] for a in range(3))
 
-    def rank_of(i, j, k):
-        return i + grid[0] * (j + grid[1] * k)
-
-    side = [-1] * 6
-    for a in range(3):
-        for s, d in ((0, -1), (1, +1)):
-            j = list(idx)
-            j[a] += d
-            if 0 <= j[a] < grid[a]:
-                side[2 * a + s] = rank_of(*j)
     origin = tuple(idx[a] * loc[a] * cell for a in range(3))
-    m = _hex(loc, cell, side=tuple(side), rank=rank, origin=origin)
+    m = _hex(loc, cell, side=_block_sides(idx, grid), rank=rank, origin=origin)
     top = m.patch_id("zmax")
     mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
     if top >= 0 and m.patchSize[top] > 0:
@@ -300,8 +303,9 @@ def cfg5_part(rank: int, n_ranks: int, decomp: str = "block", dims=(512, 512, 25
 
 def parity_parts(n_ranks: int, decomp: str):
     """A small sheared box in n_ranks partitions for the multi-rank parity checks (tests/multigpu_parity.py and the
-    parity record of bench.py): "slab" = z-slabs generated directly, "random" = a ragged blocky cellProc list
-    (random owner per 3x3x2 brick, every pair of ranks touches) through the decomposePar stand-in."""
+    parity record of bench.py): "slab" = z-slabs generated directly, "block" = structured blocks generated directly
+    (12^3 box, block_grid), "random" = a ragged blocky cellProc list (random owner per 3x3x2 brick, every pair of
+    ranks touches) through the decomposePar stand-in."""
     dims = (12, 10, 4 * max(n_ranks, 2))
     cell = 0.5e-3
     box = ((0.0, 0.0, 0.0), (dims[0] * cell, dims[1] * cell, dims[2] * cell))
@@ -312,6 +316,17 @@ def parity_parts(n_ranks: int, decomp: str):
         meshes = [M.hex_block(dims[0], dims[1], nz, (0, 0, r * nz * cell), (dims[0] * cell, dims[1] * cell, nz * cell),
                               side_nbr_rank=tuple([-1] * 4 + [r - 1 if r > 0 else -1, r + 1 if r < n_ranks - 1 else -1]),
                               my_rank=r) for r in range(n_ranks)]
+    elif decomp == "block":
+        # the structured blocks bench.py times at full size (block_grid / cfg5_part), up to three neighbours per rank
+        dims = (12, 12, 12)
+        box = ((0.0, 0.0, 0.0), (dims[0] * cell, dims[1] * cell, dims[2] * cell))
+        grid = block_grid(n_ranks, dims)
+        loc = tuple(dims[a] // grid[a] for a in range(3))
+        meshes = []
+        for r in range(n_ranks):
+            idx = (r % grid[0], (r // grid[0]) % grid[1], r // (grid[0] * grid[1]))
+            meshes.append(_hex(loc, cell, side=_block_sides(idx, grid), rank=r,
+                               origin=tuple(idx[a] * loc[a] * cell for a in range(3))))
     else:
         h = M.hex_block(*dims, length=box[1], affine=(1.0, 0.2, 0.1, 0.0, 1.0, 0.15, 0.0, 0.0, 1.0), _keep=True)
         rng = np.random.default_rng(11)

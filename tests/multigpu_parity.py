@@ -2,7 +2,7 @@
 """N-GPU parity check, one process per GPU (launch with torchrun / torch.distributed.run):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tests/multigpu_parity.py [--decomp slab|random]
+        --master-port 29511 tests/multigpu_parity.py [--decomp slab|random|block]
 
 Every rank builds all partitions (small, deterministic), runs the multi-rank oracle (in-memory halo
 copies) on the CPU, and compares its own GPU partition -- NCCL halos of U, temp, alpha1, then of
@@ -28,7 +28,7 @@ def build_parts(n_ranks, decomp):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--decomp", default="slab", choices=["slab", "random"])
+    ap.add_argument("--decomp", default="slab", choices=["slab", "random", "block"])
     args = ap.parse_args()
     import torch
     import torch.distributed as dist

@@ -154,7 +154,7 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("decomp", ["slab", "random"])
+@pytest.mark.parametrize("decomp", ["slab", "random", "block"])
 def test_two_process_gloo_halos_equal_in_process_oracle(tmp_path, decomp):
     worker = tmp_path / "worker.py"
     worker.write_text(GLOO_WORKER)
