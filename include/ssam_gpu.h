@@ -157,7 +157,11 @@ enum { SSAM_STICK_CONSTANT = 0, SSAM_STICK_EXPONENTIAL = 1 };
 
 typedef struct ssam_stick_params {
     int32_t model;     /* SSAM_STICK_*: constantSlipStick / exponentialSlipStick                  */
-    int32_t fricPatch; /* patch index of `fricPatch`; <0 skips qfric (NortonHoff case, SURVEY D-1) */
+    int32_t fricPatch; /* patch index of `fricPatch`; <0 skips qfric (NortonHoff case, SURVEY D-1).
+                        * Multi-rank: the first friction evaluation per mesh and patch all-reduces the patch centroid
+                        * (constantSlipStick.C:133-135), so EVERY rank must pass the same index, including ranks that
+                        * hold none of the patch's faces (decomposePar keeps the patch there, empty) - exactly as every
+                        * OpenFOAM rank calls reduce().  A rank passing <0 while others name a patch stalls them. */
     double betaTQ;
     double omega[3];
     double delta, muf;                    /* constantSlipStick.C:165-168                          */

@@ -289,7 +289,11 @@ def cfg5_part(rank: int, n_ranks: int, decomp: str = "block", dims=(512, 512, 25
     m = _hex(loc, cell, side=_block_sides(idx, grid), rank=rank, origin=origin)
     top = m.patch_id("zmax")
     mix = P.mixture(2700.0, AIR["rho"], 896.0, AIR["cp"], P.k_constant(167.0), P.k_constant(AIR["k"]))
-    if top >= 0 and m.patchSize[top] > 0:
+    # Every rank names the friction patch, whether or not it holds any of its faces: decomposePar keeps each physical
+    # patch on every rank (possibly empty) and every rank takes part in constantSlipStick's reduce() of the patch
+    # centroid (constantSlipStick.C:133-135).  A rank that passed "no friction patch" instead would stay out of that
+    # all-reduce and stall the others.
+    if top >= 0:
         stick = P.constant_slip_stick(top, betaTQ=0.9, delta=0.5, omega=OMEGA, muf=0.3)
         rot = P.constant_rotational_slip(top, OMEGA, 0.5, VT)
     else:

@@ -79,3 +79,21 @@ def test_parity_parts_block_runs_through_the_multirank_oracle(n_ranks):
         for f in c.outputs + [P.F_GRADU]:
             assert np.array_equal(a.field(f), b.field(f), equal_nan=True), P.FIELD_NAMES[f]
         assert np.isfinite(a.field(P.F_EPSDOT)[0]).all()
+
+
+@pytest.mark.parametrize("decomp,n_ranks", [("block", 2), ("block", 4), ("block", 8), ("slab", 2), ("slab", 4), ("slab", 8)])
+def test_every_rank_names_the_friction_patch(decomp, n_ranks):
+    """constantSlipStick's reduce() of the patch centroid (constantSlipStick.C:133-135) is a collective of ALL ranks:
+    a partition without tool faces must still pass the (empty) patch, or the ranks that own the faces wait for ever in
+    the all-reduce.  (Round 2's first 8-GPU run stalled on exactly this: the bottom blocks passed fricPatch = -1.)"""
+    dims = (8, 8, 16)
+    parts = [cases.cfg5_part(r, n_ranks, decomp, dims=dims) for r in range(n_ranks)]
+    fric = {int(c.params.stick.fricPatch) for c in parts}
+    assert len(fric) == 1 and fric.pop() >= 0
+    assert {int(c.params.stick.model) for c in parts} == {P.STICK_CONSTANT}
+    sizes = [int(c.mesh.patchSize[c.params.stick.fricPatch]) for c in parts]
+    assert sum(sizes) == dims[0] * dims[1]
+    if n_ranks == 8:
+        assert 0 in sizes  # some ranks really hold no tool face
+    # rotational-slip BC likewise present on every rank (applies to zero faces where the patch is empty)
+    assert all(c.rotslip is not None for c in parts)
