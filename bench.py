@@ -403,9 +403,12 @@ def run_gpu(args):
         thread's Python stack and ends the process instead of hanging the caller"""
         if rank == 0 or os.environ.get("SSAM_BENCH_VERBOSE"):
             log(f"[rank {rank}] phase: {name}")
-        faulthandler.cancel_dump_traceback_later()
-        if limit_s:
-            faulthandler.dump_traceback_later(limit_s, exit=True)
+        try:
+            faulthandler.cancel_dump_traceback_later()
+            if limit_s:
+                faulthandler.dump_traceback_later(limit_s, exit=True, file=sys.__stderr__)
+        except (ValueError, OSError, AttributeError):  # stderr without a file descriptor: no watchdog, never an error
+            pass
 
     # ---- parity first: nothing is timed unless the decomposed results match the oracle -------------------
     parity = None
@@ -484,6 +487,8 @@ def run_gpu(args):
     value = total_cells * args.steps / (ms_max * 1e-3) / 1e6
     sustained = total_cells * n_extra / (ms_sus * 1e-3) / 1e6
 
+    layout_dev = "tile-compact" if ctx.layout_is_compact() else "caller order"
+
     # ---- e2e: host buffers through ssam_update_fused_host, same context / same cell layout ---------------
     def e2e_leg():
         def pinned(a):
@@ -532,24 +537,13 @@ def run_gpu(args):
                 "note": "same context and cell layout as `value`; D2H = the fields the solver consumes per step "
                         "(TEqn.H:3-15,25 and thermo.nu())"}
 
-    layout_dev = "tile-compact" if ctx.layout_is_compact() else "caller order"
-    phase("e2e leg (host buffers)", 600)
-    try:
-        e2e = e2e_leg()
-    except Exception as exc:  # the device-resident line must still be printed; the failure is part of it
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "error": f"{type(exc).__name__}: {exc}"[:400]}
-        log(f"[rank {rank}] e2e leg failed: {exc}")
-        if n_ranks > 1:
-            raise  # a rank that left the collective sequence cannot be resynchronised
-    phase("fp64 ceiling + teardown", 300)
+    phase("fp64 ceiling", 300)
     fp64_peak = ctx.fp64_peak() if hasattr(ctx, "fp64_peak") else None
     transport = ctx.halo_transport()
     nvl = ctx.halo_bytes_per_update() if hasattr(ctx, "halo_bytes_per_update") else None
-    barrier()  # no rank frees buffers a neighbour may still be using
-    ctx.close()
-    phase("report", 1800 if n_ranks == 1 else 300)
 
+    # ---- the line as far as the device-resident measurement goes (rank 0); the later legs add to it ----------------
+    line, peak = None, None
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -584,25 +578,73 @@ def run_gpu(args):
                           "ms_per_step": round(ms_sus / n_extra, 4)},
             "parity": parity,
             "roofline": roof,
-            "e2e": e2e,
+            "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": "not run"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+
+    class leg:
+        """One of the legs after the timed region.  On one GPU a leg that exceeds its limit must not cost the line: a
+        timer prints what has been measured so far (naming the leg) and ends the process.  With several ranks the
+        phase watchdog applies instead (a rank cannot leave the collective sequence on its own)."""
+
+        def __init__(self, name, limit_s):
+            self.name, self.limit_s, self.timer = name, limit_s, None
+
+        def expire(self):
+            line["aborted_leg"] = f"{self.name}: no result within {self.limit_s} s"
+            print(json.dumps(line), flush=True)
+            os._exit(0)
+
+        def __enter__(self):
+            if n_ranks == 1:
+                phase(self.name, 0)
+                self.timer = threading.Timer(self.limit_s, self.expire)
+                self.timer.daemon = True
+                self.timer.start()
+            else:
+                phase(self.name, self.limit_s)
+            return self
+
+        def __exit__(self, *exc):
+            if self.timer:
+                self.timer.cancel()
+            return False
+
+    with leg("e2e leg (host buffers)", args.leg_limit or 600):
+        try:
+            e2e = e2e_leg()
+        except Exception as exc:  # the device-resident line must still be printed; the failure is part of it
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "error": f"{type(exc).__name__}: {exc}"[:400]}
+            log(f"[rank {rank}] e2e leg failed: {exc}")
+            if n_ranks > 1:
+                raise  # a rank that left the collective sequence cannot be resynchronised
+        if line is not None:
+            line["e2e"] = e2e
+    phase("teardown", 300)
+    barrier()  # no rank frees buffers a neighbour may still be using
+    ctx.close()
+    phase("report", 0 if n_ranks == 1 else 300)
+
+    if rank == 0:
         if n_ranks == 1 and not args.no_extra:
-            try:
-                line["extra_workloads"] = extra_workloads(args, stream, torch, peak)
-            except Exception as exc:
-                line["extra_workloads"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
+            with leg("extra workloads", args.leg_limit or 900):
+                try:
+                    line["extra_workloads"] = extra_workloads(args, stream, torch, peak)
+                except Exception as exc:
+                    line["extra_workloads"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
         if n_ranks == 1 and not args.no_cpu_baseline:
-            try:
-                v, threads, sample, ms = cpu_arm(args.workload, 3, 1)
-                line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port",
-                                        "sample": sample}
-            except Exception as exc:
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
-                                        "sample": f"failed: {type(exc).__name__}: {exc}"[:400]}
+            with leg("cpu baseline", args.leg_limit or 900):
+                try:
+                    v, threads, sample, ms = cpu_arm(args.workload, 3, 1)
+                    line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": threads, "kind": "port",
+                                            "sample": sample}
+                except Exception as exc:
+                    line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                            "sample": f"failed: {type(exc).__name__}: {exc}"[:400]}
         print(json.dumps(line), flush=True)
-    faulthandler.cancel_dump_traceback_later()
+    phase("done", 0)
     if n_ranks > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -641,7 +683,7 @@ def extra_workloads(args, stream, torch, peak):
     return out
 
 
-def main():
+def make_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -656,7 +698,13 @@ def main():
     ap.add_argument("--cell-kernel", type=int, default=1, choices=[0, 1, 2],
                     help="1 = tiled, one CTA per tile (default); 2 = persistent self-pipelined tiles; 0 = one thread per "
                          "cell, direct loads")
-    args = ap.parse_args()
+    ap.add_argument("--leg-limit", type=float, default=0.0,
+                    help="seconds allowed to each leg after the timed region (default: 600 e2e, 900 extras / CPU arm)")
+    return ap
+
+
+def main():
+    args = make_parser().parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
