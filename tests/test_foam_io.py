@@ -172,3 +172,83 @@ def test_reads_hand_written_v1806_decomposed_case():
         ti, tb, bc = h.read_field(os.path.join(FIX, f"processor{r}", "0", "temp"), 1)
         assert list(ti) == [(300.0, 400.0)[r]]
         assert tb[-1] == (400.0, 300.0)[r]     # processor patch: the neighbour cell's value as written
+
+
+# ---- the same two cubes in v1806's BINARY layout, emitted by an independent writer (this test, numpy.tobytes) ----------
+# binary lists are `N` newline `(` raw little-endian bytes `)` (List<T>::writeList + OSstream::write(const char*, n));
+# faces become a faceCompactList = offsets labelList + flat labels; the header carries arch "LSB;label=32;scalar=64";
+# constant/polyMesh/boundary stays ascii in every format.
+BANNER = (
+    "/*--------------------------------*- C++ -*----------------------------------*\\\n"
+    "| =========                 |                                                 |\n"
+    "| \\\\      /  F ield         | OpenFOAM: The Open Source CFD Toolbox           |\n"
+    "|  \\\\    /   O peration     | Version:  v1806                                 |\n"
+    "|   \\\\  /    A nd           | Web:      www.OpenFOAM.com                      |\n"
+    "|    \\\\/     M anipulation  |                                                 |\n"
+    "\\*---------------------------------------------------------------------------*/\n")
+RULE = "// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //\n"
+TAIL = b"\n\n// ************************************************************************* //\n"
+
+
+def _foam_header(cls, obj, location='"constant/polyMesh"', note=None):
+    s = BANNER + "FoamFile\n{\n    version     2.0;\n    format      binary;\n    class       " + cls + ";\n"
+    s += '    arch        "LSB;label=32;scalar=64";\n'
+    if note:
+        s += f'    note        "{note}";\n'
+    s += f"    location    {location};\n    object      {obj};\n}}\n" + RULE + "\n\n"
+    return s.encode()
+
+
+def _binary_list(a):
+    a = np.ascontiguousarray(a)
+    return f"{a.shape[0]}\n(".encode() + a.tobytes() + b")\n"
+
+
+def test_reads_binary_polymesh_from_an_independent_writer(tmp_path):
+    pts = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1, 2)], dtype="<f8")
+    faces = [[1, 4, 10, 7], [0, 6, 9, 3], [2, 5, 11, 8], [0, 1, 7, 6], [1, 2, 8, 7], [3, 9, 10, 4], [4, 10, 11, 5],
+             [0, 3, 4, 1], [1, 4, 5, 2], [6, 7, 10, 9], [7, 8, 11, 10]]
+    owner = np.array([0, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1], dtype="<i4")
+    note = "nPoints:12  nCells:2  nFaces:11  nInternalFaces:1"
+    pm = tmp_path / "constant" / "polyMesh"
+    pm.mkdir(parents=True)
+    (pm / "points").write_bytes(_foam_header("vectorField", "points") + _binary_list(pts) + TAIL)
+    offsets = np.cumsum([0] + [len(f) for f in faces]).astype("<i4")
+    flat = np.array([v for f in faces for v in f], dtype="<i4")
+    (pm / "faces").write_bytes(_foam_header("faceCompactList", "faces") + _binary_list(offsets) + b"\n" +
+                               _binary_list(flat) + TAIL)
+    (pm / "owner").write_bytes(_foam_header("labelList", "owner", note=note) + _binary_list(owner) + TAIL)
+    (pm / "neighbour").write_bytes(_foam_header("labelList", "neighbour", note=note) +
+                                   _binary_list(np.array([1], dtype="<i4")) + TAIL)
+    with open(os.path.join(FIX, "constant", "polyMesh", "boundary"), "rb") as fh:
+        (pm / "boundary").write_bytes(fh.read())  # ascii in every format
+
+    h = M.read_polymesh(str(pm))
+    m = h.mesh()
+    ref = M.read_polymesh(os.path.join(FIX, "constant", "polyMesh")).mesh()
+    same_mesh(m, ref, rtol=0.0)  # same numbers as the ascii files, bit for bit
+
+    # a binary volScalarField / volVectorField: `nonuniform List<scalar>` followed by the binary list
+    t0 = tmp_path / "0"
+    t0.mkdir()
+    body = (b"dimensions      [0 0 0 1 0 0 0];\n\ninternalField   nonuniform List<scalar> \n" +
+            _binary_list(np.array([300.0, 400.0], dtype="<f8")) + b";\n\nboundaryField\n{\n"
+            b"    left\n    {\n        type            fixedValue;\n        value           uniform 293;\n    }\n"
+            b"    right\n    {\n        type            zeroGradient;\n    }\n"
+            b"    walls\n    {\n        type            fixedValue;\n        value           nonuniform List<scalar> \n" +
+            _binary_list(np.arange(8, dtype="<f8") + 500.0) + b";\n    }\n}\n")
+    (t0 / "temp").write_bytes(_foam_header("volScalarField", "temp", location='"0"') + body + TAIL)
+    ti, tb, bc = h.read_field(str(t0 / "temp"), 1)
+    assert list(ti) == [300.0, 400.0]
+    assert tb[0] == 293.0 and tb[1] == 400.0 and list(tb[2:]) == [500.0 + i for i in range(8)]
+    assert list(bc) == [P.BC_VALUE, P.BC_ZERO_GRADIENT, P.BC_VALUE]
+    ubody = (b"dimensions      [0 1 -1 0 0 0 0];\n\ninternalField   nonuniform List<vector> \n" +
+             _binary_list(np.array([[1, 0, 0], [2, 0.5, 0]], dtype="<f8")) + b";\n\nboundaryField\n{\n"
+             b"    left\n    {\n        type            fixedValue;\n        value           uniform (1 0 0);\n    }\n"
+             b"    right\n    {\n        type            zeroGradient;\n    }\n"
+             b"    walls\n    {\n        type            noSlip;\n    }\n}\n")
+    (t0 / "U").write_bytes(_foam_header("volVectorField", "U", location='"0"') + ubody + TAIL)
+    ui, ub, ubc = h.read_field(str(t0 / "U"), 3)
+    assert np.array_equal(ui, [[1, 0, 0], [2, 0.5, 0]])
+    assert np.array_equal(ub[0], [1, 0, 0]) and np.array_equal(ub[1], [2, 0.5, 0]) and not ub[2:].any()
+    assert list(ubc) == [P.BC_VALUE, P.BC_ZERO_GRADIENT, P.BC_VALUE]
